@@ -1,0 +1,42 @@
+"""Shared helpers for tests: golden → oracle structures."""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from oracle.graph_oracle import OracleGraph
+
+
+def golden_state(z, tag):
+    pre = tag + "/"
+    keys = ("alpha", "linear.weight", "linear.bias")
+    out = {}
+    for k in z.files:
+        if k.startswith(pre):
+            name = k[len(pre):]
+            if name in keys or name.startswith("layers."):
+                out[name] = torch.from_numpy(z[k])
+    return out
+
+
+def golden_grads(z, tag):
+    pre = tag + "/grad/"
+    return {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+
+
+def golden_graph(z, prefix="graph/", num_genes=None):
+    node_id = torch.from_numpy(z[prefix + "node_id"])
+    g = int((node_id >= 0).sum()) if num_genes is None else num_genes
+    return OracleGraph(g, node_id.shape[0] - g, torch.from_numpy(z[prefix + "src"]),
+                       torch.from_numpy(z[prefix + "dst"]), torch.from_numpy(z[prefix + "weight"]),
+                       node_id, torch.from_numpy(z[prefix + "features"]))
+
+
+def golden_csr(z, pre="x"):
+    return sp.csr_matrix((z[pre + "_data"], z[pre + "_indices"], z[pre + "_indptr"]), shape=tuple(z[pre + "_shape"]))
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| — logits can be ≈0 so element-wise relative error is ill-posed."""
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
