@@ -1,0 +1,130 @@
+/*
+ * wsage.h — C ABI of the B200-native weighted-GraphSAGE hot path (libwsage.so).
+ *
+ * Drop-in boundary for scDeepSort's edge-weighted message passing.  The reference has no
+ * FFI of its own: the path is reached through Python (DGL 0.4.3 UDF protocol), so each
+ * entry point cites the reference code it replaces.  All pointers are DEVICE pointers owned
+ * by the caller (the library allocates nothing persistent); every call is asynchronous on
+ * the caller's CUDA stream (`stream` is a cudaStream_t passed as void*); the library is
+ * stateless and re-entrant.  Every function returns a status code (0 = ok) and never
+ * throws; wsage_last_error() returns a thread-local message for the last non-zero status.
+ *
+ * Feature matrices are row-major [n_rows, dim] with a leading dimension `ld*` given in
+ * ELEMENTS (ld >= dim), fp32.  Rows must be 4-byte aligned; 16-byte aligned rows with
+ * dim % 4 == 0 take the vectorised path.
+ */
+#ifndef WSAGE_H
+#define WSAGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSAGE_OK            0
+#define WSAGE_EINVAL        1   /* bad argument (null pointer, negative size, ...)        */
+#define WSAGE_EUNSUPPORTED  2   /* shape/dtype/alignment this build has no kernel for      */
+#define WSAGE_ECUDA         3   /* a CUDA runtime call failed; see wsage_last_error()      */
+
+#define WSAGE_COL_I32  32
+#define WSAGE_COL_U16  16
+
+/* Library / ABI version (major*1000 + minor). */
+int wsage_version(void);
+/* Thread-local, never NULL. */
+const char* wsage_last_error(void);
+/* Number of kernels this library has launched from the calling thread since the last reset
+ * (bench.py's `gpu_launches`). */
+int64_t wsage_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------
+ * Generic NodeFlow block (any sampled or full-neighbour block).
+ *
+ * Replaces, for one block: GNN.message_func (/root/reference/models/gnn.py:47-56, incl. the
+ * host np.where α-index cascade and its two D2H syncs), fn.mean('m','neigh')
+ * (models/gnn.py:65) and the DGL 0.4.3 src-gather / copy-reduce kernels behind
+ * nf.block_compute.  The per-edge message tensor is never materialised.
+ *
+ *   out[v,:] = (1 / max(deg(v),1)) * SUM_{e in row v} w[e] * alpha[k(e)] * h_src[col[e],:]
+ *   k(e) = src_id>=0 && dst_id<0 ? src_id : dst_id>=0 && src_id<0 ? dst_id
+ *        : dst_id>=0 && src_id>=0 ? gene_num : gene_num+1
+ *
+ * CSR is destination-major: rowptr[n_dst+1] (int64), col[E] = local source index, w[E] =
+ * edata['weight'].  src_id / dst_id are ndata['id'] of the source / destination layer
+ * (int32; gene -> gene index, cell -> -1).  alpha is the [gene_num+2] parameter.
+ * ------------------------------------------------------------------------------------- */
+int wsage_block_agg_fwd(const int64_t* rowptr, const int32_t* col, const float* w,
+                        const int32_t* src_id, const int32_t* dst_id,
+                        const float* alpha, int32_t gene_num,
+                        const float* h_src, int64_t ld_src, int64_t n_src,
+                        float* out, int64_t ld_out, int64_t n_dst, int32_t dim,
+                        void* stream);
+
+/* Backward of wsage_block_agg_fwd (replaces torch autograd through the DGL UDF, i.e. the
+ * scatter of models/gnn.py:54-56 and the index of self.alpha at :54).
+ *   d_h_src[col[e],:] += s_v * w[e] * alpha[k(e)] * d_out[v,:]          (may be NULL)
+ *   d_alpha[k(e)]     += s_v * w[e] * <h_src[col[e],:], d_out[v,:]>     (may be NULL)
+ * Both outputs are ACCUMULATED with atomics; the caller zero-initialises them. */
+int wsage_block_agg_bwd(const int64_t* rowptr, const int32_t* col, const float* w,
+                        const int32_t* src_id, const int32_t* dst_id,
+                        const float* alpha, int32_t gene_num,
+                        const float* h_src, int64_t ld_src, int64_t n_src,
+                        const float* d_out, int64_t ld_dout, int64_t n_dst, int32_t dim,
+                        float* d_h_src, int64_t ld_dh, float* d_alpha,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Full-graph bipartite pass (the throughput path; same reference lines as above, applied to
+ * every destination of one kind at once instead of per 500-seed NodeFlow).
+ *
+ *   acc[v,:] = SUM_{e in row v} x[e] * hs[col[e],:]
+ *   out[v,:] = dscale[v] * acc[v,:] + selfcoef[v] * hself[v,:]      (each term optional)
+ *   raw[v,:] = acc[v,:]                                              (optional)
+ *   dot[v]   = <acc[v,:], q[v,:]>                                    (optional)
+ *
+ * x holds RAW expression values; the reference's per-destination normalisation
+ * (utils/preprocess_internal.py:15-23), the mean's 1/(deg+1), alpha and the self-loop
+ * (preprocess_internal.py:213-214) enter through dscale / selfcoef and a pre-scaled hs, so one
+ * CSR per direction serves forward and backward.  col is int32 or uint16 (col_bits), sorted
+ * ascending inside each row.  row_perm (optional, int32[n_dst]) gives the order in which
+ * destination rows are assigned to warps (load balancing); output rows are NOT permuted.
+ * algo: 0 = auto, 1 = gather (L2 gather, warp per row), 2 = tiled (source windows staged in
+ * shared memory by bulk-async copies, register-stationary destination tiles).
+ * workspace: wsage_spmm_workspace_bytes() bytes of scratch (may be NULL when that is 0).
+ * ------------------------------------------------------------------------------------- */
+typedef struct wsage_spmm_args {
+    const int64_t* rowptr;      /* [n_dst+1]                                            */
+    const void*    col;         /* [nnz] int32 or uint16                                */
+    int32_t        col_bits;    /* WSAGE_COL_I32 | WSAGE_COL_U16                        */
+    const float*   x;           /* [nnz]                                                */
+    const float*   hs;          /* [n_src, dim] source table                            */
+    int64_t        ld_hs;
+    int64_t        n_src;
+    int64_t        n_dst;
+    int32_t        dim;
+    const float*   dscale;      /* [n_dst] or NULL (=1)                                 */
+    const float*   selfcoef;    /* [n_dst] or NULL (no self term)                       */
+    const float*   hself;       /* [n_dst, dim] (required iff selfcoef)                 */
+    int64_t        ld_hself;
+    float*         out;         /* [n_dst, dim] or NULL                                 */
+    int64_t        ld_out;
+    float*         raw;         /* [n_dst, dim] or NULL                                 */
+    int64_t        ld_raw;
+    const float*   q;           /* [n_dst, dim] (required iff dot)                      */
+    int64_t        ld_q;
+    float*         dot;         /* [n_dst] or NULL                                      */
+    const int32_t* row_perm;    /* [n_dst] or NULL                                      */
+    int32_t        algo;
+    void*          workspace;
+    size_t         workspace_bytes;
+} wsage_spmm_args;
+
+size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a);
+int wsage_spmm(const wsage_spmm_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSAGE_H */

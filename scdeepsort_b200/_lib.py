@@ -1,0 +1,84 @@
+"""ctypes binding of ``libwsage.so`` (the C ABI in ``include/wsage.h``).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, the
+caller gets a ``RuntimeError``.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C scdeepsort_b200/csrc``.
+"""
+import ctypes
+import subprocess
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = CSRC / "libwsage.so"
+
+OK, EINVAL, EUNSUPPORTED, ECUDA = 0, 1, 2, 3
+COL_I32, COL_U16 = 32, 16
+ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
+
+EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
+           "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm")
+
+
+class SpmmArgs(Structure):
+    """Mirror of ``wsage_spmm_args`` (include/wsage.h)."""
+    _fields_ = [
+        ("rowptr", c_void_p), ("col", c_void_p), ("col_bits", c_int32), ("x", c_void_p),
+        ("hs", c_void_p), ("ld_hs", c_int64), ("n_src", c_int64), ("n_dst", c_int64), ("dim", c_int32),
+        ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
+        ("out", c_void_p), ("ld_out", c_int64), ("raw", c_void_p), ("ld_raw", c_int64),
+        ("q", c_void_p), ("ld_q", c_int64), ("dot", c_void_p), ("row_perm", c_void_p),
+        ("algo", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libwsage.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    proc = subprocess.run(["make", "-C", str(CSRC)], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"building libwsage.so failed:\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `make -C scdeepsort_b200/csrc` or __graft_entry__.build()). "
+            "scdeepsort_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    lib.wsage_version.restype = c_int32
+    lib.wsage_last_error.restype = c_char_p
+    lib.wsage_launch_count.restype = c_int64
+    lib.wsage_launch_count.argtypes = [c_int32]
+    lib.wsage_block_agg_fwd.restype = c_int32
+    lib.wsage_block_agg_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                        c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]
+    lib.wsage_block_agg_bwd.restype = c_int32
+    lib.wsage_block_agg_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                        c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
+                                        c_void_p, c_int64, c_void_p, c_void_p]
+    lib.wsage_spmm_workspace_bytes.restype = c_size_t
+    lib.wsage_spmm_workspace_bytes.argtypes = [POINTER(SpmmArgs)]
+    lib.wsage_spmm.restype = c_int32
+    lib.wsage_spmm.argtypes = [POINTER(SpmmArgs), c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != OK:
+        msg = load().wsage_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {rc}: {msg}")
+
+
+def launch_count(reset=False):
+    return int(load().wsage_launch_count(1 if reset else 0))

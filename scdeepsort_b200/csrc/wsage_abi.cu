@@ -1,0 +1,115 @@
+// extern "C" entry points of libwsage.so (declared in include/wsage.h).
+#include "agg_gather.cuh"
+#include "agg_tiled.cuh"
+
+using namespace wsage;
+
+extern "C" {
+
+int wsage_version(void) { return 1000; }
+
+const char* wsage_last_error(void) { return g_err; }
+
+int64_t wsage_launch_count(int reset) {
+    const int64_t n = g_launches;
+    if (reset) g_launches = 0;
+    return n;
+}
+
+int wsage_block_agg_fwd(const int64_t* rowptr, const int32_t* col, const float* w,
+                        const int32_t* src_id, const int32_t* dst_id,
+                        const float* alpha, int32_t gene_num,
+                        const float* h_src, int64_t ld_src, int64_t n_src,
+                        float* out, int64_t ld_out, int64_t n_dst, int32_t dim,
+                        void* stream) {
+    WSAGE_REQUIRE(n_dst >= 0 && n_src >= 0 && dim > 0, "negative size or dim <= 0");
+    if (n_dst == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(rowptr && out, "null rowptr/out");
+    WSAGE_REQUIRE(ld_src >= dim && ld_out >= dim, "leading dimension < dim");
+    WSAGE_REQUIRE((src_id && dst_id && alpha) || (!src_id && !dst_id), "src_id, dst_id and alpha go together");
+    GatherParams p{};
+    p.rowptr = rowptr; p.col = col; p.w = w;
+    p.src_id = src_id; p.dst_id = dst_id; p.alpha = alpha; p.gene_num = gene_num;
+    p.hs = h_src; p.ld_hs = ld_src; p.n_dst = n_dst; p.dim = dim; p.mean = 1;
+    p.out = out; p.ld_out = ld_out;
+    const bool vec4 = dim % 4 == 0 && ld_src % 4 == 0 && ld_out % 4 == 0 && aligned16(h_src) && aligned16(out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return src_id ? launch_gather_fwd<int32_t, true>(p, vec4, st) : launch_gather_fwd<int32_t, false>(p, vec4, st);
+}
+
+int wsage_block_agg_bwd(const int64_t* rowptr, const int32_t* col, const float* w,
+                        const int32_t* src_id, const int32_t* dst_id,
+                        const float* alpha, int32_t gene_num,
+                        const float* h_src, int64_t ld_src, int64_t n_src,
+                        const float* d_out, int64_t ld_dout, int64_t n_dst, int32_t dim,
+                        float* d_h_src, int64_t ld_dh, float* d_alpha,
+                        void* stream) {
+    WSAGE_REQUIRE(n_dst >= 0 && n_src >= 0 && dim > 0, "negative size or dim <= 0");
+    if (n_dst == 0 || (!d_h_src && !d_alpha)) return WSAGE_OK;
+    WSAGE_REQUIRE(rowptr && d_out && src_id && dst_id && alpha, "null argument");
+    WSAGE_REQUIRE(!d_alpha || h_src, "d_alpha needs h_src");
+    WSAGE_REQUIRE(ld_dout >= dim && (!d_h_src || ld_dh >= dim) && (!h_src || ld_src >= dim), "leading dimension < dim");
+    GatherBwdParams p{};
+    p.rowptr = rowptr; p.col = col; p.w = w;
+    p.src_id = src_id; p.dst_id = dst_id; p.alpha = alpha; p.gene_num = gene_num;
+    p.hs = h_src; p.ld_hs = ld_src; p.dout = d_out; p.ld_dout = ld_dout;
+    p.n_dst = n_dst; p.dim = dim; p.dh = d_h_src; p.ld_dh = ld_dh; p.dalpha = d_alpha;
+    const bool vec4 = dim % 4 == 0 && ld_src % 4 == 0 && ld_dout % 4 == 0 && ld_dh % 4 == 0 &&
+                      aligned16(h_src) && aligned16(d_out) && aligned16(d_h_src);
+    return launch_gather_bwd(p, vec4, static_cast<cudaStream_t>(stream));
+}
+
+static int spmm_validate(const wsage_spmm_args* a) {
+    WSAGE_REQUIRE(a != nullptr, "null args");
+    WSAGE_REQUIRE(a->n_dst >= 0 && a->n_src >= 0 && a->dim > 0, "negative size or dim <= 0");
+    WSAGE_REQUIRE(a->col_bits == WSAGE_COL_I32 || a->col_bits == WSAGE_COL_U16, "col_bits must be 16 or 32");
+    WSAGE_REQUIRE(a->col_bits == WSAGE_COL_I32 || a->n_src <= 65536, "uint16 columns need n_src <= 65536");
+    WSAGE_REQUIRE(a->algo >= 0 && a->algo <= 2, "algo must be 0, 1 or 2");
+    if (a->n_dst == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(a->rowptr && a->hs, "null rowptr/hs");
+    WSAGE_REQUIRE(a->out || a->raw || a->dot, "no output requested");
+    WSAGE_REQUIRE(a->ld_hs >= a->dim, "ld_hs < dim");
+    WSAGE_REQUIRE(!a->selfcoef || (a->hself && a->ld_hself >= a->dim), "selfcoef needs hself");
+    WSAGE_REQUIRE(!a->dot || (a->q && a->ld_q >= a->dim), "dot needs q");
+    WSAGE_REQUIRE(!a->out || a->ld_out >= a->dim, "ld_out < dim");
+    WSAGE_REQUIRE(!a->raw || a->ld_raw >= a->dim, "ld_raw < dim");
+    return WSAGE_OK;
+}
+
+static bool spmm_vec4(const wsage_spmm_args* a) {
+    return a->dim % 4 == 0 && a->ld_hs % 4 == 0 && aligned16(a->hs) &&
+           (!a->out || (a->ld_out % 4 == 0 && aligned16(a->out))) &&
+           (!a->raw || (a->ld_raw % 4 == 0 && aligned16(a->raw))) &&
+           (!a->hself || (a->ld_hself % 4 == 0 && aligned16(a->hself))) &&
+           (!a->q || (a->ld_q % 4 == 0 && aligned16(a->q)));
+}
+
+size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a) {
+    if (!a || spmm_validate(a) != WSAGE_OK || a->n_dst == 0) return 0;
+    return tiled_workspace_bytes(a, spmm_vec4(a));
+}
+
+int wsage_spmm(const wsage_spmm_args* a, void* stream) {
+    const int rc = spmm_validate(a);
+    if (rc != WSAGE_OK) return rc;
+    if (a->n_dst == 0) return WSAGE_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec4 = spmm_vec4(a);
+    int algo = a->algo;
+    if (algo == 0) algo = tiled_profitable(a, vec4) ? 2 : 1;
+    if (algo == 2) {
+        if (!tiled_supported(a, vec4))
+            return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "tiled kernel needs dim % 4 == 0, contiguous 16-byte aligned hs and dim <= 512");
+        return launch_tiled(a, st);
+    }
+    GatherParams p{};
+    p.rowptr = a->rowptr; p.col = a->col; p.w = a->x;
+    p.hs = a->hs; p.ld_hs = a->ld_hs; p.n_dst = a->n_dst; p.dim = a->dim; p.mean = 0;
+    p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
+    p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
+    p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot; p.row_perm = a->row_perm;
+    return a->col_bits == WSAGE_COL_U16 ? launch_gather_fwd<uint16_t, false>(p, vec4, st)
+                                        : launch_gather_fwd<int32_t, false>(p, vec4, st);
+}
+
+}  // extern "C"

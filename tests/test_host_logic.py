@@ -1,0 +1,179 @@
+"""CPU-only checks: the C-ABI library loads and exports what include/wsage.h declares, and the
+host-side graph / mini-batch logic matches the oracle's restatement of the reference contract."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle
+from scds_helpers import golden_csr, golden_graph
+
+import scdeepsort_b200 as sd
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "wsage.h").read_text()
+    declared = set(re.findall(r"\b(wsage_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(sd._lib.EXPORTS)
+    lib = sd._lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.wsage_version() >= 1000
+    assert lib.wsage_last_error() is not None
+
+
+def test_spmm_args_struct_layout_matches_header():
+    header = (ROOT / "include" / "wsage.h").read_text()
+    body = header[header.index("typedef struct wsage_spmm_args {"):header.index("} wsage_spmm_args;")]
+    names = re.findall(r"\b([a-z_]+);", body)
+    assert names == [f[0] for f in sd._lib.SpmmArgs._fields_]
+
+
+def test_argument_errors_are_reported_not_thrown():
+    lib = sd._lib.load()
+    a = sd._lib.SpmmArgs()
+    a.n_dst, a.n_src, a.dim, a.col_bits = 4, 4, 0, 32
+    import ctypes
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL
+    assert b"dim" in lib.wsage_last_error()
+    a.dim, a.col_bits, a.n_src = 8, 16, 70000
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL
+    assert b"uint16" in lib.wsage_last_error()
+    with pytest.raises(RuntimeError):
+        sd._lib.check(sd._lib.EINVAL, "x")
+
+
+def test_model_refuses_cpu():
+    m = sd.GNN(8, 4, 3, 1, 10, activation=torch.relu)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(object())
+
+
+def test_state_dict_keys_match_reference(golden_train):
+    z = golden_train
+    m = sd.GNN(int(z["dense_dim"]), int(z["hidden"]), int(z["num_labels"]), 2, int(z["num_genes"]), activation=torch.relu)
+    ref = {k[len("L2/"):]: z[k].shape for k in z.files
+           if k.startswith("L2/") and (k.startswith("L2/layers.") or k in ("L2/alpha", "L2/linear.weight", "L2/linear.bias"))}
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert mine == ref
+    assert torch.all(m.alpha == 1)
+
+
+def _edge_set(rowptr, src, w, n):
+    deg = (rowptr[1:] - rowptr[:-1])
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    key = dst * n + src
+    o = torch.argsort(key)
+    return key[o], w[o]
+
+
+def test_graph_builder_matches_oracle(golden_test):
+    z = golden_test
+    og = graph_oracle.build_graph(golden_csr(z), golden_csr(z, "xt"))
+    g = sd.DeepSortGraph.from_expression(golden_csr(z), golden_csr(z, "xt"))
+    n = og.num_nodes
+    assert g.number_of_nodes() == n and g.number_of_edges() == og.src.shape[0]
+    k1, w1 = _edge_set(g.in_rowptr, g.in_src, g.in_weight, n)
+    o = torch.argsort(og.dst * n + og.src)
+    assert torch.equal(k1, (og.dst * n + og.src)[o])
+    assert float(((w1 - og.weight[o]).abs() / og.weight[o]).max()) < 4e-7
+    assert torch.equal(g.ndata["id"], og.node_id)
+    # from_edges on the reference's own arrays gives the same CSR
+    gg = golden_graph(z, num_genes=int(z["num_genes"]))
+    g2 = sd.DeepSortGraph.from_edges(gg.src, gg.dst, gg.weight, gg.node_id, gg.features, gg.num_genes)
+    k2, w2 = _edge_set(g2.in_rowptr, g2.in_src, g2.in_weight, n)
+    assert torch.equal(k1, k2)
+
+
+def test_bipartite_factorisation_reproduces_reference_weights(golden_train):
+    z = golden_train
+    x = golden_csr(z)
+    bg = sd.BipartiteGraph.from_expression(x)
+    gg = golden_graph(z)
+    G = bg.num_genes
+    # gene→cell edges: w = x * norm_c ;  cell→gene edges: w = x * norm_g
+    cs = bg.cell_csr
+    col = torch.from_numpy(cs.col.numpy().view(np.uint16).astype(np.int64))
+    deg = cs.rowptr[1:] - cs.rowptr[:-1]
+    row = torch.repeat_interleave(torch.arange(bg.num_cells), deg)
+    w = cs.x * bg.norm_c[row]
+    n = gg.num_nodes
+    key = (row + G) * n + col
+    mask = (gg.dst >= G) & (gg.src < G)
+    rkey = (gg.dst * n + gg.src)[mask]
+    o1, o2 = torch.argsort(key), torch.argsort(rkey)
+    assert torch.equal(key[o1], rkey[o2])
+    assert float(((w[o1] - gg.weight[mask][o2]).abs() / gg.weight[mask][o2]).max()) < 5e-7
+    assert torch.allclose(bg.mean_c, 1.0 / (deg + 1).float())
+    gs = bg.gene_csr
+    degg = gs.rowptr[1:] - gs.rowptr[:-1]
+    rowg = torch.repeat_interleave(torch.arange(G), degg)
+    colg = gs.col.to(torch.int64) if gs.col_bits == 32 else torch.from_numpy(gs.col.numpy().view(np.uint16).astype(np.int64))
+    wg = gs.x * bg.norm_g[rowg]
+    keyg = rowg * n + (colg + G)
+    maskg = (gg.dst < G) & (gg.src >= G)
+    rkeyg = (gg.dst * n + gg.src)[maskg]
+    o1, o2 = torch.argsort(keyg), torch.argsort(rkeyg)
+    assert torch.equal(keyg[o1], rkeyg[o2])
+    assert float(((wg[o1] - gg.weight[maskg][o2]).abs() / gg.weight[maskg][o2]).max()) < 5e-7
+    assert int((degg == 0).sum()) > 0 and torch.all(bg.norm_g[degg == 0] == 0)
+    # columns ascending inside each row; permutation is a permutation
+    assert torch.equal(torch.sort(cs.row_perm.long()).values, torch.arange(bg.num_cells))
+    d = col[1:] - col[:-1]
+    inner = torch.ones_like(d, dtype=torch.bool)
+    inner[(cs.rowptr[1:-1] - 1).clamp(min=0)] = False
+    assert torch.all(d[inner] > 0)
+
+
+@pytest.mark.parametrize("n_layers", [1, 2])
+def test_sampler_full_neighbour_matches_oracle_flow(golden_train, n_layers):
+    z = golden_train
+    gg = golden_graph(z)
+    g = sd.DeepSortGraph.from_edges(gg.src, gg.dst, gg.weight, gg.node_id, gg.features, gg.num_genes)
+    seeds = torch.from_numpy(z["train_ids"])[:37]
+    nf = next(iter(sd.NeighborSampler(g, 37, g.number_of_nodes(), n_layers, 'in', shuffle=False, num_workers=8,
+                                      seed_nodes=seeds)))
+    nf.copy_from_parent()
+    of = graph_oracle.full_neighbor_flow(gg, seeds, n_layers)
+    assert nf.num_layers == n_layers + 1
+    for i in range(n_layers + 1):
+        assert torch.equal(nf.layer_parent_nid(i), of.layer_nid[i])
+        assert torch.equal(nf.layers[i].data["id"], of.layer_id[i])
+    assert torch.equal(nf.layers[0].data["features"], of.features)
+    for i in range(n_layers):
+        b, ob = nf.blocks[i], of.blocks[i]
+        assert (b.n_src, b.n_dst) == (ob.n_src, ob.n_dst)
+        dst = torch.repeat_interleave(torch.arange(b.n_dst), b.rowptr[1:] - b.rowptr[:-1])
+        k1 = dst * b.n_src + b.col.long(); k2 = ob.dst * ob.n_src + ob.src
+        o1, o2 = torch.argsort(k1), torch.argsort(k2)
+        assert torch.equal(k1[o1], k2[o2]) and torch.equal(b.weight[o1], ob.weight[o2])
+
+
+def test_sampler_batches_shuffle_and_fanout(golden_train):
+    z = golden_train
+    gg = golden_graph(z)
+    g = sd.DeepSortGraph.from_edges(gg.src, gg.dst, gg.weight, gg.node_id, gg.features, gg.num_genes)
+    seeds = torch.from_numpy(z["train_ids"])
+    gen = torch.Generator().manual_seed(3)
+    sampler = sd.NeighborSampler(g, 50, 7, 2, 'in', shuffle=True, seed_nodes=seeds, generator=gen)
+    seen = []
+    for nf in sampler:
+        seen.append(nf.layer_parent_nid(-1))
+        for i, b in enumerate(nf.blocks):
+            deg = b.rowptr[1:] - b.rowptr[:-1]
+            full = (g.in_rowptr[1:] - g.in_rowptr[:-1])[nf.layer_parent_nid(i + 1)]
+            assert torch.equal(deg, torch.clamp(full, max=7))            # ≤ fanout, without replacement
+            eid = nf.block_parent_eid(i)
+            assert eid.unique().shape[0] == eid.shape[0]
+            # every sampled edge really is an in-edge of its destination, weight untouched
+            dst = torch.repeat_interleave(nf.layer_parent_nid(i + 1), deg)
+            assert torch.all((eid >= g.in_rowptr[dst]) & (eid < g.in_rowptr[dst + 1]))
+            assert torch.equal(b.weight, g.in_weight[eid])
+            assert torch.equal(nf.layer_parent_nid(i)[b.col.long()], g.in_src[eid])
+    assert len(seen) == len(sampler) == (len(seeds) + 49) // 50
+    allseen = torch.cat(seen)
+    assert torch.equal(torch.sort(allseen).values, torch.sort(seeds).values) and not torch.equal(allseen, seeds)
