@@ -35,7 +35,7 @@ extern "C" {
 int wsage_version(void);
 /* Thread-local, never NULL. */
 const char* wsage_last_error(void);
-/* Number of kernels this library has launched from the calling thread since the last reset
+/* Number of kernels this library has launched in this process since the last reset
  * (bench.py's `gpu_launches`). */
 int64_t wsage_launch_count(int reset);
 
@@ -99,6 +99,7 @@ typedef struct wsage_spmm_args {
     const void*    col;         /* [nnz] int32 or uint16                                */
     int32_t        col_bits;    /* WSAGE_COL_I32 | WSAGE_COL_U16                        */
     const float*   x;           /* [nnz]                                                */
+    int64_t        nnz;         /* = rowptr[n_dst]; lets algo 0 pick a kernel without a device read */
     const float*   hs;          /* [n_src, dim] source table                            */
     int64_t        ld_hs;
     int64_t        n_src;

@@ -23,7 +23,7 @@ EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_blo
 class SpmmArgs(Structure):
     """Mirror of ``wsage_spmm_args`` (include/wsage.h)."""
     _fields_ = [
-        ("rowptr", c_void_p), ("col", c_void_p), ("col_bits", c_int32), ("x", c_void_p),
+        ("rowptr", c_void_p), ("col", c_void_p), ("col_bits", c_int32), ("x", c_void_p), ("nnz", c_int64),
         ("hs", c_void_p), ("ld_hs", c_int64), ("n_src", c_int64), ("n_dst", c_int64), ("dim", c_int32),
         ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
         ("out", c_void_p), ("ld_out", c_int64), ("raw", c_void_p), ("ld_raw", c_int64),

@@ -1,12 +1,378 @@
-// "tiled" aggregation kernel (placeholder until the TMA-window kernel lands).
+// "tiled" aggregation kernel for the full-graph bipartite pass (sm_100a).
+//
+//   acc[v,:] = SUM_{e in row v} x[e] * hs[col[e],:]        (+ epilogue, see wsage_spmm)
+//
+// The gather kernel re-reads a source row from L2 once per EDGE.  Here a CTA owns a tile of
+// NW*R destination rows whose accumulators stay in registers, and streams the source table
+// through shared memory in windows of W consecutive rows: columns are sorted inside each CSR
+// row, so the rows a window needs are exactly one contiguous [W, dim] slab of hs, fetched by a
+// single bulk-async copy (cp.async.bulk, completion on an mbarrier) into a ring of S stages.
+// Every source row is thus read from L2/HBM once per TILE and then served to all its edges
+// from shared memory (16-byte conflict-free LDS), cutting L2->SM traffic by the average
+// number of tile rows that reference a source row.
+//
+//   warp NW (producer): one elected lane waits empty[s], arms full[s] with the byte count and
+//                       issues the bulk copy of window w into stage s.
+//   warps 0..NW-1     : each owns R destination rows; per window waits full[s], consumes the
+//                       edges of its rows whose column falls in the window, arrives on empty[s].
+//
+// Rows are dealt to tiles/warps in stripes of the (degree-sorted) row_perm so that every tile
+// and every warp gets the same mix of heavy and light rows.  The source dimension can be split
+// (n_splits > 1, for few-but-long rows such as gene destinations): partial sums then go to the
+// workspace and tiled_reduce_kernel finishes deterministically (fixed summation order).
 #pragma once
 #include "common.cuh"
 
 namespace wsage {
-inline size_t tiled_workspace_bytes(const wsage_spmm_args*, bool) { return 0; }
-inline bool tiled_supported(const wsage_spmm_args*, bool) { return false; }
-inline bool tiled_profitable(const wsage_spmm_args*, bool) { return false; }
-inline int launch_tiled(const wsage_spmm_args*, cudaStream_t) {
-    return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "tiled kernel not built");
+
+constexpr int kTiledStages = 4;
+constexpr int kTiledSmemBudget = 200 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
+
+struct TiledParams {
+    const int64_t* rowptr;
+    const void* col;
+    const float* x;
+    const float* hs;          // contiguous [n_src, dim]
+    int64_t n_src;
+    int64_t n_dst;
+    int dim;
+    int win_rows;             // W
+    int n_windows;            // ceil(n_src / W)
+    int n_tiles;
+    int n_splits;
+    int win_per_split;
+    const int32_t* row_perm;
+    // epilogue (n_splits == 1) ...
+    const float* dscale;
+    const float* selfcoef;
+    const float* hself;
+    int64_t ld_hself;
+    float* out;
+    int64_t ld_out;
+    float* raw;
+    int64_t ld_raw;
+    const float* q;
+    int64_t ld_q;
+    float* dot;
+    // ... or partial sums (n_splits > 1): partial[split][row][dim]
+    float* partial;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Final per-row epilogue shared by the tiled kernel (n_splits == 1) and the split reducer.
+template <int J>
+__device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t v, const float4 (&acc)[J], int lane) {
+    const float scale = p.dscale ? p.dscale[v] : 1.f;
+    const float sc = p.selfcoef ? p.selfcoef[v] : 0.f;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c >= p.dim) continue;
+        if (p.raw) *reinterpret_cast<float4*>(p.raw + v * p.ld_raw + c) = acc[j];
+        if (p.dot) dot += Vec<4>::dot(acc[j], __ldg(reinterpret_cast<const float4*>(p.q + v * p.ld_q + c)));
+        if (p.out) {
+            float4 o = Vec<4>::scale(scale, acc[j]);
+            if (p.selfcoef) Vec<4>::fma(o, sc, __ldg(reinterpret_cast<const float4*>(p.hself + v * p.ld_hself + c)));
+            *reinterpret_cast<float4*>(p.out + v * p.ld_out + c) = o;
+        }
+    }
+    if (p.dot) {
+        dot = warp_sum(dot);
+        if (lane == 0) p.dot[v] = dot;
+    }
+}
+
+template <typename ColT, int J, int NW, int R>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+agg_tiled_kernel(const TiledParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kTiledStages];
+    __shared__ uint64_t empty_bar[kTiledStages];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x % p.n_tiles;
+    const int split = blockIdx.x / p.n_tiles;
+    const int w_begin = split * p.win_per_split;
+    const int w_end = min(p.n_windows, w_begin + p.win_per_split);
+    const size_t stage_floats = (size_t)p.win_rows * p.dim;
+    float* stages = reinterpret_cast<float*>(smem_raw);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTiledStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ------------------------------- producer -------------------------------------------
+        if (lane == 0) {
+            for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
+                const int s = it % kTiledStages;
+                const uint32_t ph = (it / kTiledStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int64_t row0 = (int64_t)w * p.win_rows;
+                const int64_t rows = min((int64_t)p.win_rows, p.n_src - row0);
+                const uint32_t bytes = (uint32_t)(rows * p.dim * sizeof(float));
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                bulk_g2s(stages + s * stage_floats, p.hs + row0 * p.dim, bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ----------------------------------- consumers ------------------------------------------
+    const ColT* __restrict__ col = static_cast<const ColT*>(p.col);
+    int64_t row[R];      // destination row (or -1)
+    int64_t beg[R];      // first edge of the row
+    int len[R];          // edges in the row
+    int cur[R];          // next unconsumed edge (relative to beg)
+    int ccol[R];         // this lane's column of the current 32-edge chunk
+    float cx[R];         // this lane's value of the current chunk
+    float4 acc[R][J];
+
+    auto load_chunk = [&](int r) {
+        const int e = (cur[r] & ~31) + lane;
+        if (e < len[r]) {
+            ccol[r] = (int)col[beg[r] + e];
+            cx[r] = p.x[beg[r] + e];
+        } else {
+            ccol[r] = 0x7fffffff;
+            cx[r] = 0.f;
+        }
+    };
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t i = (int64_t)(r * NW + warp) * p.n_tiles + tile;     // striped deal of sorted rows
+        row[r] = -1; beg[r] = 0; len[r] = 0; cur[r] = 0;
+        if (i < p.n_dst) {
+            row[r] = p.row_perm ? (int64_t)p.row_perm[i] : i;
+            beg[r] = p.rowptr[row[r]];
+            len[r] = (int)(p.rowptr[row[r] + 1] - beg[r]);
+            if (w_begin > 0) {     // split > 0: first edge with col >= first column of this split
+                const int64_t first_col = (int64_t)w_begin * p.win_rows;
+                int lo = 0, hi = len[r];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((int64_t)col[beg[r] + mid] < first_col) lo = mid + 1; else hi = mid;
+                }
+                cur[r] = lo;
+            }
+        }
+        load_chunk(r);
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
+        const int s = it % kTiledStages;
+        const uint32_t ph = (it / kTiledStages) & 1;
+        const int win_base = w * p.win_rows;
+        const int win_end = win_base + p.win_rows;
+        const float* stage = stages + s * stage_floats;
+        mbar_wait(&full_bar[s], ph);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            while (true) {
+                const int l0 = cur[r] & 31;
+                const unsigned m = __ballot_sync(0xffffffffu, lane >= l0 && ccol[r] < win_end);
+                const int cnt = __popc(m);         // columns ascend: a contiguous run starting at lane l0
+                for (int k = 0; k < cnt; k += 2) {
+                    const int c0 = __shfl_sync(0xffffffffu, ccol[r], l0 + k);
+                    const float x0 = __shfl_sync(0xffffffffu, cx[r], l0 + k);
+                    const bool two = k + 1 < cnt;
+                    const int c1 = two ? __shfl_sync(0xffffffffu, ccol[r], (l0 + k + 1) & 31) : c0;
+                    const float x1 = two ? __shfl_sync(0xffffffffu, cx[r], (l0 + k + 1) & 31) : 0.f;
+                    const float* s0 = stage + (size_t)(c0 - win_base) * p.dim + lane * 4;
+                    const float* s1 = stage + (size_t)(c1 - win_base) * p.dim + lane * 4;
+                    float4 v0[J], v1[J];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const bool on = (j * 32 + lane) * 4 < p.dim;
+                        v0[j] = on ? *reinterpret_cast<const float4*>(s0 + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v1[j] = on ? *reinterpret_cast<const float4*>(s1 + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        Vec<4>::fma(acc[r][j], x0, v0[j]);
+                        Vec<4>::fma(acc[r][j], x1, v1[j]);
+                    }
+                }
+                cur[r] += cnt;
+                if (cnt == 0 || (cur[r] & 31) != 0) break;
+                load_chunk(r);      // chunk used up: fetch the next one (all-sentinel past the row end),
+                                    // the window may continue in it
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    // ------------------------------------ epilogue -------------------------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (row[r] < 0) continue;
+        if (p.n_splits == 1) {
+            tiled_row_epilogue<J>(p, row[r], acc[r], lane);
+        } else {
+            float* dst = p.partial + ((size_t)split * p.n_dst + row[r]) * p.dim;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int c = (j * 32 + lane) * 4;
+                if (c < p.dim) *reinterpret_cast<float4*>(dst + c) = acc[r][j];
+            }
+        }
+    }
+}
+
+// Sums the split partials in fixed order and applies the epilogue: one warp per row.
+template <int J>
+__global__ void __launch_bounds__(256)
+tiled_reduce_kernel(const TiledParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t v = warp0; v < p.n_dst; v += nwarps) {
+        float4 acc[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < p.n_splits; ++s) {
+            const float* src = p.partial + ((size_t)s * p.n_dst + v) * p.dim;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int c = (j * 32 + lane) * 4;
+                if (c < p.dim) {
+                    const float4 t = *reinterpret_cast<const float4*>(src + c);
+                    acc[j].x += t.x; acc[j].y += t.y; acc[j].z += t.z; acc[j].w += t.w;
+                }
+            }
+        }
+        tiled_row_epilogue<J>(p, v, acc, lane);
+    }
+}
+
+// ------------------------------------------ host side ------------------------------------------
+constexpr int kTiledNW = 12;   // consumer warps per CTA
+constexpr int kTiledR = 4;     // destination rows per warp
+
+struct TiledPlan {
+    int win_rows, n_windows, n_tiles, n_splits, win_per_split;
+    size_t smem_bytes, workspace_bytes;
+};
+
+inline bool tiled_supported(const wsage_spmm_args* a, bool vec4) {
+    return vec4 && a->dim <= 512 && a->ld_hs == a->dim && a->n_src < (int64_t)0x7fffffff &&
+           a->n_dst < (int64_t)0x7fffffff && (int64_t)a->dim * 4 * 8 <= kTiledSmemBudget / kTiledStages;
+}
+
+inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
+    TiledPlan pl{};
+    const int rows_per_tile = kTiledNW * kTiledR;
+    const size_t row_bytes = (size_t)a->dim * sizeof(float);
+    int w = (int)(kTiledSmemBudget / kTiledStages / row_bytes);
+    if ((int64_t)w > a->n_src) w = (int)(a->n_src > 0 ? a->n_src : 1);
+    pl.win_rows = w;
+    pl.n_windows = (int)((a->n_src + w - 1) / w);
+    pl.n_tiles = (int)((a->n_dst + rows_per_tile - 1) / rows_per_tile);
+    // enough CTAs for >= ~6 waves of 148 when rows are few but long (gene destinations)
+    int splits = (6 * kNumSMs + pl.n_tiles - 1) / pl.n_tiles;
+    const int max_splits = pl.n_windows / 8 > 0 ? pl.n_windows / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    pl.win_per_split = (pl.n_windows + splits - 1) / splits;
+    pl.n_splits = (pl.n_windows + pl.win_per_split - 1) / pl.win_per_split;
+    pl.smem_bytes = (size_t)kTiledStages * w * row_bytes;
+    pl.workspace_bytes = pl.n_splits > 1 ? (size_t)pl.n_splits * a->n_dst * a->dim * sizeof(float) : 0;
+    return pl;
+}
+
+inline size_t tiled_workspace_bytes(const wsage_spmm_args* a, bool vec4) {
+    if (a->algo == 1 || !tiled_supported(a, vec4)) return 0;
+    return tiled_plan(a).workspace_bytes;
+}
+
+// Worth it when a source row is referenced by >= ~1.5 rows of a tile on average (then staging it
+// once per tile moves fewer bytes out of L2 than gathering it once per edge) and there are enough
+// rows to fill the machine; otherwise the L2 gather kernel wins.
+inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
+    if (!tiled_supported(a, vec4) || a->n_src == 0 || a->n_dst == 0) return false;
+    const double avg_deg = (double)a->nnz / (double)a->n_dst;
+    const double reuse = avg_deg * kTiledNW * kTiledR / (double)a->n_src;
+    // Measured on B200 (profiles/r01_microbench.md): a source table that fits L2 (< ~48 MB) is
+    // gathered at the L2->SM fabric rate (~17 TB/s), which the tiled kernel does not beat yet.
+    const double table_bytes = (double)a->n_src * a->dim * sizeof(float);
+    return reuse >= 1.5 && a->nnz >= (int64_t)1 << 20 && table_bytes >= 48.0 * (1 << 20);
+}
+
+template <typename ColT, int J>
+int launch_tiled_j(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
+    TiledParams p{};
+    p.rowptr = a->rowptr; p.col = a->col; p.x = a->x; p.hs = a->hs;
+    p.n_src = a->n_src; p.n_dst = a->n_dst; p.dim = a->dim;
+    p.win_rows = pl.win_rows; p.n_windows = pl.n_windows; p.n_tiles = pl.n_tiles;
+    p.n_splits = pl.n_splits; p.win_per_split = pl.win_per_split; p.row_perm = a->row_perm;
+    p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
+    p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
+    p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
+    p.partial = static_cast<float*>(a->workspace);
+    auto kern = agg_tiled_kernel<ColT, J, kTiledNW, kTiledR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_tiled)", cudaGetErrorString(e));
+    kern<<<pl.n_tiles * pl.n_splits, (kTiledNW + 1) * 32, pl.smem_bytes, st>>>(p);
+    int rc = check_launch("agg_tiled");
+    if (rc != WSAGE_OK || pl.n_splits == 1) return rc;
+    tiled_reduce_kernel<J><<<gather_grid(a->n_dst), 256, 0, st>>>(p);
+    return check_launch("tiled_reduce");
+}
+
+inline int launch_tiled(const wsage_spmm_args* a, cudaStream_t st) {
+    const TiledPlan pl = tiled_plan(a);
+    if (pl.workspace_bytes > a->workspace_bytes || (pl.workspace_bytes && !a->workspace))
+        return fail(WSAGE_EINVAL, "%s: %s", "wsage_spmm", "workspace too small (see wsage_spmm_workspace_bytes)");
+    const int J = (a->dim + 127) / 128;
+    const bool u16 = a->col_bits == WSAGE_COL_U16;
+#define WSAGE_TILED_CASE(JJ)                                                         \
+    case JJ: return u16 ? launch_tiled_j<uint16_t, JJ>(a, pl, st) : launch_tiled_j<int32_t, JJ>(a, pl, st);
+    switch (J) {
+        WSAGE_TILED_CASE(1)
+        WSAGE_TILED_CASE(2)
+        WSAGE_TILED_CASE(3)
+        WSAGE_TILED_CASE(4)
+    }
+#undef WSAGE_TILED_CASE
+    return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "dim > 512");
+}
+
 }  // namespace wsage

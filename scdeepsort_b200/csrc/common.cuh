@@ -1,6 +1,7 @@
 // Shared host/device helpers for libwsage (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -12,7 +13,7 @@ namespace wsage {
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 inline thread_local char g_err[512] = "";
-inline thread_local int64_t g_launches = 0;
+inline std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs backward on its own thread
 
 inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
     snprintf(g_err, sizeof(g_err), fmt, a, b);

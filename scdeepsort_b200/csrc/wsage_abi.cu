@@ -11,9 +11,7 @@ int wsage_version(void) { return 1000; }
 const char* wsage_last_error(void) { return g_err; }
 
 int64_t wsage_launch_count(int reset) {
-    const int64_t n = g_launches;
-    if (reset) g_launches = 0;
-    return n;
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int wsage_block_agg_fwd(const int64_t* rowptr, const int32_t* col, const float* w,
@@ -65,6 +63,7 @@ static int spmm_validate(const wsage_spmm_args* a) {
     WSAGE_REQUIRE(a->col_bits == WSAGE_COL_I32 || a->col_bits == WSAGE_COL_U16, "col_bits must be 16 or 32");
     WSAGE_REQUIRE(a->col_bits == WSAGE_COL_I32 || a->n_src <= 65536, "uint16 columns need n_src <= 65536");
     WSAGE_REQUIRE(a->algo >= 0 && a->algo <= 2, "algo must be 0, 1 or 2");
+    WSAGE_REQUIRE(a->nnz >= 0, "negative nnz");
     if (a->n_dst == 0) return WSAGE_OK;
     WSAGE_REQUIRE(a->rowptr && a->hs, "null rowptr/hs");
     WSAGE_REQUIRE(a->out || a->raw || a->dot, "no output requested");

@@ -129,7 +129,7 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
         raw = torch.empty(csr.n_dst, dim, device=dev, dtype=torch.float32)
     dot = torch.empty(csr.n_dst, device=dev, dtype=torch.float32) if want_dot else None
     a = _lib.SpmmArgs()
-    a.rowptr, a.col, a.col_bits, a.x = _ptr(csr.rowptr), _ptr(csr.col), csr.col_bits, _ptr(csr.x)
+    a.rowptr, a.col, a.col_bits, a.x, a.nnz = _ptr(csr.rowptr), _ptr(csr.col), csr.col_bits, _ptr(csr.x), csr.nnz
     a.hs, a.ld_hs, a.n_src, a.n_dst, a.dim = _ptr(hs), hs.stride(0), csr.n_src, csr.n_dst, dim
     if dscale is not None:
         _check_vec(dscale, "dscale", torch.float32, csr.n_dst)
