@@ -123,6 +123,8 @@ typedef struct wsage_spmm_args {
 } wsage_spmm_args;
 
 size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a);
+/* The kernel wsage_spmm would run for these arguments: 1 (gather) or 2 (tiled); 0 on bad args. */
+int wsage_spmm_algo(const wsage_spmm_args* a);
 int wsage_spmm(const wsage_spmm_args* a, void* stream);
 
 #ifdef __cplusplus

@@ -6,20 +6,27 @@
 // NW*R destination rows whose accumulators stay in registers, and streams the source table
 // through shared memory in windows of W consecutive rows: columns are sorted inside each CSR
 // row, so the rows a window needs are exactly one contiguous [W, dim] slab of hs, fetched by a
-// single bulk-async copy (cp.async.bulk, completion on an mbarrier) into a ring of S stages.
-// Every source row is thus read from L2/HBM once per TILE and then served to all its edges
-// from shared memory (16-byte conflict-free LDS), cutting L2->SM traffic by the average
-// number of tile rows that reference a source row.
+// single bulk-async copy (cp.async.bulk, completion on an mbarrier; SASS UBLKCP) into a ring of
+// S stages.  Every source row is thus read from L2 once per TILE and then served to all its
+// edges from shared memory (16-byte conflict-free LDS).
 //
 //   warp NW (producer): one elected lane waits empty[s], arms full[s] with the byte count and
 //                       issues the bulk copy of window w into stage s.
 //   warps 0..NW-1     : each owns R destination rows; per window waits full[s], consumes the
 //                       edges of its rows whose column falls in the window, arrives on empty[s].
 //
-// Rows are dealt to tiles/warps in stripes of the (degree-sorted) row_perm so that every tile
-// and every warp gets the same mix of heavy and light rows.  The source dimension can be split
-// (n_splits > 1, for few-but-long rows such as gene destinations): partial sums then go to the
-// workspace and tiled_reduce_kernel finishes deterministically (fixed summation order).
+// Scheduling.  A tile is NW*R CONSECUTIVE rows of row_perm (rows sorted by degree), so the
+// warps of a CTA see the same edge density and stay in step on the stage ring; the degree skew
+// (gene rows: 3 % .. 100 % dense) is absorbed across CTAs instead: the source dimension is cut
+// into n_splits window ranges, CTAs are ordered split-major / heavy-tile-first, partial sums of
+// split tiles go to the workspace and tiled_reduce_kernel adds them in fixed order
+// (deterministic).  Split-major order also means the ~148 resident CTAs stream the SAME slice
+// of the source table (<= ~40 MB, L2-resident) at the same time, so HBM sees each source row
+// about once even when the table (cells: 1.2 GB) is far larger than L2.
+//
+// DIM is a compile-time feature width (0 = runtime width, predicated loads) so the hot loop has
+// no per-chunk predicates: a 400-float row is 3 full float4 chunks per lane plus one scalar
+// chunk on lanes 0..15 (13 shared-memory wavefronts per edge, the minimum for 1600 B).
 #pragma once
 #include "common.cuh"
 
@@ -27,6 +34,8 @@ namespace wsage {
 
 constexpr int kTiledStages = 4;
 constexpr int kTiledSmemBudget = 200 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
+constexpr int kTiledNW = 12;                   // consumer warps per CTA
+constexpr int kTiledR = 4;                     // destination rows per warp
 
 struct TiledParams {
     const int64_t* rowptr;
@@ -84,22 +93,62 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// How a DIM-float row is spread over the 32 lanes of a warp.
+template <int DIM>
+struct RowShape {
+    static constexpr int J4 = DIM > 0 ? DIM / 128 : 0;            // float4 chunks used by all 32 lanes
+    static constexpr int REM = DIM > 0 ? DIM - J4 * 128 : 0;      // floats left over
+    static constexpr bool TAIL4 = REM > 32;                       // partial float4 chunk: lanes < REM/4
+    static constexpr bool TAIL1 = REM > 0 && REM <= 32;           // scalar chunk: lanes < REM
+    static constexpr int N4 = DIM > 0 ? J4 + (TAIL4 ? 1 : 0) : 4;  // runtime width: 4 predicated chunks (<= 512)
+    static_assert(DIM % 4 == 0, "feature width must be a multiple of 4");
+
+    static __device__ __forceinline__ bool on4(int j, int lane, int dim) {
+        if (DIM > 0) return j < J4 || lane < REM / 4;
+        return (j * 32 + lane) * 4 < dim;
+    }
+    static __device__ __forceinline__ bool on1(int lane) { return lane < REM; }
+};
+
+template <int DIM>
+struct RowAcc {
+    using S = RowShape<DIM>;
+    float4 v4[S::N4];
+    float v1;
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int j = 0; j < S::N4; ++j) v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1 = 0.f;
+    }
+};
+
 // Final per-row epilogue shared by the tiled kernel (n_splits == 1) and the split reducer.
-template <int J>
-__device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t v, const float4 (&acc)[J], int lane) {
+template <int DIM>
+__device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t v, const RowAcc<DIM>& a, int lane) {
+    using S = RowShape<DIM>;
     const float scale = p.dscale ? p.dscale[v] : 1.f;
     const float sc = p.selfcoef ? p.selfcoef[v] : 0.f;
     float dot = 0.f;
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
+    for (int j = 0; j < S::N4; ++j) {
+        if (!S::on4(j, lane, p.dim)) continue;
         const int c = (j * 32 + lane) * 4;
-        if (c >= p.dim) continue;
-        if (p.raw) *reinterpret_cast<float4*>(p.raw + v * p.ld_raw + c) = acc[j];
-        if (p.dot) dot += Vec<4>::dot(acc[j], __ldg(reinterpret_cast<const float4*>(p.q + v * p.ld_q + c)));
+        if (p.raw) *reinterpret_cast<float4*>(p.raw + v * p.ld_raw + c) = a.v4[j];
+        if (p.dot) dot += Vec<4>::dot(a.v4[j], __ldg(reinterpret_cast<const float4*>(p.q + v * p.ld_q + c)));
         if (p.out) {
-            float4 o = Vec<4>::scale(scale, acc[j]);
+            float4 o = Vec<4>::scale(scale, a.v4[j]);
             if (p.selfcoef) Vec<4>::fma(o, sc, __ldg(reinterpret_cast<const float4*>(p.hself + v * p.ld_hself + c)));
             *reinterpret_cast<float4*>(p.out + v * p.ld_out + c) = o;
+        }
+    }
+    if (S::TAIL1 && S::on1(lane)) {
+        const int c = S::J4 * 128 + lane;
+        if (p.raw) p.raw[v * p.ld_raw + c] = a.v1;
+        if (p.dot) dot += a.v1 * __ldg(p.q + v * p.ld_q + c);
+        if (p.out) {
+            float o = scale * a.v1;
+            if (p.selfcoef) o = fmaf(sc, __ldg(p.hself + v * p.ld_hself + c), o);
+            p.out[v * p.ld_out + c] = o;
         }
     }
     if (p.dot) {
@@ -108,20 +157,22 @@ __device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t
     }
 }
 
-template <typename ColT, int J, int NW, int R>
+template <typename ColT, int DIM, int NW, int R>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 agg_tiled_kernel(const TiledParams p) {
+    using S = RowShape<DIM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kTiledStages];
     __shared__ uint64_t empty_bar[kTiledStages];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x % p.n_tiles;
-    const int split = blockIdx.x / p.n_tiles;
+    const int tile = blockIdx.x % p.n_tiles;          // split-major launch order: CTAs that are resident
+    const int split = blockIdx.x / p.n_tiles;         // together stream the same slice of hs
     const int w_begin = split * p.win_per_split;
     const int w_end = min(p.n_windows, w_begin + p.win_per_split);
-    const size_t stage_floats = (size_t)p.win_rows * p.dim;
+    const int dim = DIM > 0 ? DIM : p.dim;
+    const size_t stage_floats = (size_t)p.win_rows * dim;
     float* stages = reinterpret_cast<float*>(smem_raw);
 
     if (threadIdx.x == 0) {
@@ -143,9 +194,9 @@ agg_tiled_kernel(const TiledParams p) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 const int64_t row0 = (int64_t)w * p.win_rows;
                 const int64_t rows = min((int64_t)p.win_rows, p.n_src - row0);
-                const uint32_t bytes = (uint32_t)(rows * p.dim * sizeof(float));
+                const uint32_t bytes = (uint32_t)(rows * dim * sizeof(float));
                 mbar_arrive_expect_tx(&full_bar[s], bytes);
-                bulk_g2s(stages + s * stage_floats, p.hs + row0 * p.dim, bytes, &full_bar[s]);
+                bulk_g2s(stages + s * stage_floats, p.hs + row0 * dim, bytes, &full_bar[s]);
             }
         }
         return;
@@ -157,42 +208,55 @@ agg_tiled_kernel(const TiledParams p) {
     int64_t beg[R];      // first edge of the row
     int len[R];          // edges in the row
     int cur[R];          // next unconsumed edge (relative to beg)
-    int ccol[R];         // this lane's column of the current 32-edge chunk
-    float cx[R];         // this lane's value of the current chunk
-    float4 acc[R][J];
+    int ccol[R], ncol[R];   // this lane's column in the current / prefetched 32-edge chunk
+    float cx[R], nx[R];     // this lane's value   in the current / prefetched chunk
+    RowAcc<DIM> acc[R];
 
-    auto load_chunk = [&](int r) {
-        const int e = (cur[r] & ~31) + lane;
+    // lane-private fetch of edge (chunk_base + lane); sentinel past the row end
+    auto fetch = [&](int r, int chunk_base, int& c_out, float& x_out) {
+        const int e = chunk_base + lane;
         if (e < len[r]) {
-            ccol[r] = (int)col[beg[r] + e];
-            cx[r] = p.x[beg[r] + e];
+            c_out = (int)col[beg[r] + e];
+            x_out = p.x[beg[r] + e];
         } else {
-            ccol[r] = 0x7fffffff;
-            cx[r] = 0.f;
+            c_out = 0x7fffffff;
+            x_out = 0.f;
         }
     };
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int64_t i = (int64_t)(r * NW + warp) * p.n_tiles + tile;     // striped deal of sorted rows
+        const int64_t i = ((int64_t)tile * NW + warp) * R + r;      // consecutive rows of row_perm
         row[r] = -1; beg[r] = 0; len[r] = 0; cur[r] = 0;
         if (i < p.n_dst) {
             row[r] = p.row_perm ? (int64_t)p.row_perm[i] : i;
             beg[r] = p.rowptr[row[r]];
             len[r] = (int)(p.rowptr[row[r] + 1] - beg[r]);
-            if (w_begin > 0) {     // split > 0: first edge with col >= first column of this split
-                const int64_t first_col = (int64_t)w_begin * p.win_rows;
+        }
+        acc[r].zero();
+    }
+    if (w_begin > 0) {
+        // first edge with col >= first column of this split: lane r searches row r, then broadcast
+        const int64_t first_col = (int64_t)w_begin * p.win_rows;
+        int found = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (lane == r) {
                 int lo = 0, hi = len[r];
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if ((int64_t)col[beg[r] + mid] < first_col) lo = mid + 1; else hi = mid;
                 }
-                cur[r] = lo;
+                found = lo;
             }
         }
-        load_chunk(r);
 #pragma unroll
-        for (int j = 0; j < J; ++j) acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < R; ++r) cur[r] = __shfl_sync(0xffffffffu, found, r);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        fetch(r, cur[r] & ~31, ccol[r], cx[r]);
+        fetch(r, (cur[r] & ~31) + 32, ncol[r], nx[r]);
     }
 
     for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
@@ -200,7 +264,7 @@ agg_tiled_kernel(const TiledParams p) {
         const uint32_t ph = (it / kTiledStages) & 1;
         const int win_base = w * p.win_rows;
         const int win_end = win_base + p.win_rows;
-        const float* stage = stages + s * stage_floats;
+        const float* stage = stages + s * stage_floats + lane * 4 - (size_t)win_base * dim;
         mbar_wait(&full_bar[s], ph);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -211,28 +275,40 @@ agg_tiled_kernel(const TiledParams p) {
                 for (int k = 0; k < cnt; k += 2) {
                     const int c0 = __shfl_sync(0xffffffffu, ccol[r], l0 + k);
                     const float x0 = __shfl_sync(0xffffffffu, cx[r], l0 + k);
-                    const bool two = k + 1 < cnt;
-                    const int c1 = two ? __shfl_sync(0xffffffffu, ccol[r], (l0 + k + 1) & 31) : c0;
-                    const float x1 = two ? __shfl_sync(0xffffffffu, cx[r], (l0 + k + 1) & 31) : 0.f;
-                    const float* s0 = stage + (size_t)(c0 - win_base) * p.dim + lane * 4;
-                    const float* s1 = stage + (size_t)(c1 - win_base) * p.dim + lane * 4;
-                    float4 v0[J], v1[J];
+                    int c1 = __shfl_sync(0xffffffffu, ccol[r], (l0 + k + 1) & 31);
+                    float x1 = __shfl_sync(0xffffffffu, cx[r], (l0 + k + 1) & 31);
+                    if (k + 1 >= cnt) { c1 = c0; x1 = 0.f; }       // odd tail: re-read edge 0 with weight 0
+                    const float* s0 = stage + (size_t)c0 * dim;
+                    const float* s1 = stage + (size_t)c1 * dim;
+                    float4 a4[S::N4], b4[S::N4];
+                    float a1 = 0.f, b1 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const bool on = (j * 32 + lane) * 4 < p.dim;
-                        v0[j] = on ? *reinterpret_cast<const float4*>(s0 + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v1[j] = on ? *reinterpret_cast<const float4*>(s1 + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < S::N4; ++j) {
+                        if (S::on4(j, lane, dim)) {
+                            a4[j] = *reinterpret_cast<const float4*>(s0 + j * 128);
+                            b4[j] = *reinterpret_cast<const float4*>(s1 + j * 128);
+                        }
+                    }
+                    if (S::TAIL1 && S::on1(lane)) {
+                        a1 = s0[S::J4 * 128 - lane * 3];           // column J4*128 + lane (s0 already has +4*lane)
+                        b1 = s1[S::J4 * 128 - lane * 3];
                     }
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        Vec<4>::fma(acc[r][j], x0, v0[j]);
-                        Vec<4>::fma(acc[r][j], x1, v1[j]);
+                    for (int j = 0; j < S::N4; ++j) {
+                        if (S::on4(j, lane, dim)) {
+                            Vec<4>::fma(acc[r].v4[j], x0, a4[j]);
+                            Vec<4>::fma(acc[r].v4[j], x1, b4[j]);
+                        }
                     }
+                    if (S::TAIL1) acc[r].v1 = fmaf(x1, b1, fmaf(x0, a1, acc[r].v1));
                 }
                 cur[r] += cnt;
                 if (cnt == 0 || (cur[r] & 31) != 0) break;
-                load_chunk(r);      // chunk used up: fetch the next one (all-sentinel past the row end),
-                                    // the window may continue in it
+                // chunk used up: the prefetched one becomes current (all-sentinel past the row
+                // end) and the one after it is requested; the window may continue in it
+                ccol[r] = ncol[r];
+                cx[r] = nx[r];
+                fetch(r, cur[r] + 32, ncol[r], nx[r]);
             }
         }
         __syncwarp();
@@ -244,48 +320,42 @@ agg_tiled_kernel(const TiledParams p) {
     for (int r = 0; r < R; ++r) {
         if (row[r] < 0) continue;
         if (p.n_splits == 1) {
-            tiled_row_epilogue<J>(p, row[r], acc[r], lane);
+            tiled_row_epilogue<DIM>(p, row[r], acc[r], lane);
         } else {
-            float* dst = p.partial + ((size_t)split * p.n_dst + row[r]) * p.dim;
+            float* dst = p.partial + ((size_t)split * p.n_dst + row[r]) * dim;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int c = (j * 32 + lane) * 4;
-                if (c < p.dim) *reinterpret_cast<float4*>(dst + c) = acc[r][j];
-            }
+            for (int j = 0; j < S::N4; ++j)
+                if (S::on4(j, lane, dim)) *reinterpret_cast<float4*>(dst + (j * 32 + lane) * 4) = acc[r].v4[j];
+            if (S::TAIL1 && S::on1(lane)) dst[S::J4 * 128 + lane] = acc[r].v1;
         }
     }
 }
 
 // Sums the split partials in fixed order and applies the epilogue: one warp per row.
-template <int J>
 __global__ void __launch_bounds__(256)
 tiled_reduce_kernel(const TiledParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
     for (int64_t v = warp0; v < p.n_dst; v += nwarps) {
-        float4 acc[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        RowAcc<0> acc;
+        acc.zero();
         for (int s = 0; s < p.n_splits; ++s) {
             const float* src = p.partial + ((size_t)s * p.n_dst + v) * p.dim;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 const int c = (j * 32 + lane) * 4;
                 if (c < p.dim) {
                     const float4 t = *reinterpret_cast<const float4*>(src + c);
-                    acc[j].x += t.x; acc[j].y += t.y; acc[j].z += t.z; acc[j].w += t.w;
+                    acc.v4[j].x += t.x; acc.v4[j].y += t.y; acc.v4[j].z += t.z; acc.v4[j].w += t.w;
                 }
             }
         }
-        tiled_row_epilogue<J>(p, v, acc, lane);
+        tiled_row_epilogue<0>(p, v, acc, lane);
     }
 }
 
 // ------------------------------------------ host side ------------------------------------------
-constexpr int kTiledNW = 12;   // consumer warps per CTA
-constexpr int kTiledR = 4;     // destination rows per warp
-
 struct TiledPlan {
     int win_rows, n_windows, n_tiles, n_splits, win_per_split;
     size_t smem_bytes, workspace_bytes;
@@ -305,11 +375,15 @@ inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
     pl.win_rows = w;
     pl.n_windows = (int)((a->n_src + w - 1) / w);
     pl.n_tiles = (int)((a->n_dst + rows_per_tile - 1) / rows_per_tile);
-    // enough CTAs for >= ~6 waves of 148 when rows are few but long (gene destinations)
-    int splits = (6 * kNumSMs + pl.n_tiles - 1) / pl.n_tiles;
+    // (a) each split's slice of hs should stay L2-resident while the resident CTAs stream it
+    const double table_bytes = (double)a->n_src * row_bytes;
+    int splits = (int)((table_bytes + 40.0 * (1 << 20) - 1) / (40.0 * (1 << 20)));
+    // (b) >= ~48 waves of work units so the heaviest tile (degree-sorted, skewed) cannot dominate
+    const int balance = (48 * kNumSMs + pl.n_tiles - 1) / pl.n_tiles;
+    if (balance > splits) splits = balance;
     const int max_splits = pl.n_windows / 8 > 0 ? pl.n_windows / 8 : 1;
     if (splits > max_splits) splits = max_splits;
-    if (splits > 64) splits = 64;
+    if (splits > 256) splits = 256;
     if (splits < 1) splits = 1;
     pl.win_per_split = (pl.n_windows + splits - 1) / splits;
     pl.n_splits = (pl.n_windows + pl.win_per_split - 1) / pl.win_per_split;
@@ -324,20 +398,17 @@ inline size_t tiled_workspace_bytes(const wsage_spmm_args* a, bool vec4) {
 }
 
 // Worth it when a source row is referenced by >= ~1.5 rows of a tile on average (then staging it
-// once per tile moves fewer bytes out of L2 than gathering it once per edge) and there are enough
-// rows to fill the machine; otherwise the L2 gather kernel wins.
+// once per tile moves fewer bytes out of L2 than gathering it once per edge) and there is enough
+// work to amortise the pipeline; otherwise the L2 gather kernel wins.
 inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
     if (!tiled_supported(a, vec4) || a->n_src == 0 || a->n_dst == 0) return false;
     const double avg_deg = (double)a->nnz / (double)a->n_dst;
     const double reuse = avg_deg * kTiledNW * kTiledR / (double)a->n_src;
-    // Measured on B200 (profiles/r01_microbench.md): a source table that fits L2 (< ~48 MB) is
-    // gathered at the L2->SM fabric rate (~17 TB/s), which the tiled kernel does not beat yet.
-    const double table_bytes = (double)a->n_src * a->dim * sizeof(float);
-    return reuse >= 1.5 && a->nnz >= (int64_t)1 << 20 && table_bytes >= 48.0 * (1 << 20);
+    return reuse >= 1.5 && a->nnz >= (int64_t)1 << 20;
 }
 
-template <typename ColT, int J>
-int launch_tiled_j(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
+template <typename ColT, int DIM>
+int launch_tiled_dim(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
     TiledParams p{};
     p.rowptr = a->rowptr; p.col = a->col; p.x = a->x; p.hs = a->hs;
     p.n_src = a->n_src; p.n_dst = a->n_dst; p.dim = a->dim;
@@ -347,32 +418,31 @@ int launch_tiled_j(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t s
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
     p.partial = static_cast<float*>(a->workspace);
-    auto kern = agg_tiled_kernel<ColT, J, kTiledNW, kTiledR>;
+    auto kern = agg_tiled_kernel<ColT, DIM, kTiledNW, kTiledR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_tiled)", cudaGetErrorString(e));
     kern<<<pl.n_tiles * pl.n_splits, (kTiledNW + 1) * 32, pl.smem_bytes, st>>>(p);
     int rc = check_launch("agg_tiled");
     if (rc != WSAGE_OK || pl.n_splits == 1) return rc;
-    tiled_reduce_kernel<J><<<gather_grid(a->n_dst), 256, 0, st>>>(p);
+    tiled_reduce_kernel<<<gather_grid(a->n_dst), 256, 0, st>>>(p);
     return check_launch("tiled_reduce");
+}
+
+template <typename ColT>
+int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
+    switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and the bench (400/400)
+        case 400: return launch_tiled_dim<ColT, 400>(a, pl, st);
+        case 200: return launch_tiled_dim<ColT, 200>(a, pl, st);
+        case 128: return launch_tiled_dim<ColT, 128>(a, pl, st);
+        default:  return launch_tiled_dim<ColT, 0>(a, pl, st);
+    }
 }
 
 inline int launch_tiled(const wsage_spmm_args* a, cudaStream_t st) {
     const TiledPlan pl = tiled_plan(a);
     if (pl.workspace_bytes > a->workspace_bytes || (pl.workspace_bytes && !a->workspace))
         return fail(WSAGE_EINVAL, "%s: %s", "wsage_spmm", "workspace too small (see wsage_spmm_workspace_bytes)");
-    const int J = (a->dim + 127) / 128;
-    const bool u16 = a->col_bits == WSAGE_COL_U16;
-#define WSAGE_TILED_CASE(JJ)                                                         \
-    case JJ: return u16 ? launch_tiled_j<uint16_t, JJ>(a, pl, st) : launch_tiled_j<int32_t, JJ>(a, pl, st);
-    switch (J) {
-        WSAGE_TILED_CASE(1)
-        WSAGE_TILED_CASE(2)
-        WSAGE_TILED_CASE(3)
-        WSAGE_TILED_CASE(4)
-    }
-#undef WSAGE_TILED_CASE
-    return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "dim > 512");
+    return a->col_bits == WSAGE_COL_U16 ? launch_tiled_col<uint16_t>(a, pl, st) : launch_tiled_col<int32_t>(a, pl, st);
 }
 
 }  // namespace wsage

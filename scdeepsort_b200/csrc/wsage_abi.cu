@@ -88,6 +88,12 @@ size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a) {
     return tiled_workspace_bytes(a, spmm_vec4(a));
 }
 
+int wsage_spmm_algo(const wsage_spmm_args* a) {
+    if (!a || spmm_validate(a) != WSAGE_OK) return 0;
+    if (a->algo != 0) return a->algo;
+    return tiled_profitable(a, spmm_vec4(a)) ? 2 : 1;
+}
+
 int wsage_spmm(const wsage_spmm_args* a, void* stream) {
     const int rc = spmm_validate(a);
     if (rc != WSAGE_OK) return rc;

@@ -12,6 +12,9 @@ import torch
 from . import _lib
 
 
+TIMING = None     # set to a list by bench.py to collect per-launch CUDA-event timings of wsage_spmm
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -154,5 +157,14 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
     nbytes = lib.wsage_spmm_workspace_bytes(ctypes.byref(a))
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8) if nbytes else None
     a.workspace, a.workspace_bytes = _ptr(ws), nbytes
-    _lib.check(lib.wsage_spmm(ctypes.byref(a), _stream()), "wsage_spmm")
+    if TIMING is None:
+        _lib.check(lib.wsage_spmm(ctypes.byref(a), _stream()), "wsage_spmm")
+    else:       # bench.py: per-launch CUDA events on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.wsage_spmm(ctypes.byref(a), _stream()), "wsage_spmm")
+        e1.record()
+        TIMING.append(dict(algo=int(lib.wsage_spmm_algo(ctypes.byref(a))), n_dst=csr.n_dst, n_src=csr.n_src,
+                           nnz=csr.nnz, dim=dim, col_bits=csr.col_bits, self=selfcoef is not None,
+                           n_out=int(out is not None) + int(raw is not None), dot=want_dot, events=(e0, e1)))
     return out, raw, dot

@@ -1,0 +1,128 @@
+"""Cell-sharded data parallelism for the full-graph path.  One process per GPU.
+
+Cells (rows of X, their CSR edges, feature rows, labels) are partitioned contiguously over
+ranks; gene-side state (gene features/activations, α, all weights) is replicated.  The only
+data-path exchange is where genes aggregate over ALL cells:
+
+  forward   S_g = Σ_ranks Σ_{c in shard} x_cg·h_c         → all-reduce(sum) of [G, D] per gene layer
+  backward  of that all-reduce is an all-reduce of the incoming gradient — only reached when the
+            cell features feeding it require grad (layers ≥ 2)
+  grads     loss is a SUM over cells (train.py:36), and back-propagation is linear in the
+            incoming gradient, so each rank back-propagates its own cells' partial gradient
+            through the replicated gene-side ops and ONE all-reduce(sum) of the flattened
+            parameter gradients gives the exact full-batch gradient.
+
+The reference has no distributed code at all (no NCCL/Gloo call sites); this is new surface.
+Communication helpers here are backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
+"""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .gnn import GNN, _CellAggregate
+from .graph import BipartiteGraph
+from .ops import Csr
+
+
+def is_dist():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def cell_ranges(num_cells: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced partition of cell indices: rank r owns [lo, hi)."""
+    base, rem = divmod(num_cells, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def globalize_gene_normalisers(graph: BipartiteGraph):
+    """deg_g and Σ_c x_cg are sums over ALL cells: all-reduce the shard-local partials once and
+    rebuild ``norm_g`` / ``mean_g`` (utils/preprocess_internal.py:15-23 applied to the whole atlas)."""
+    deg = graph.local_deg_g.to(torch.float64).clone()
+    colsum = graph.local_colsum_g.to(torch.float64).clone()
+    if is_dist():
+        dist.all_reduce(deg)
+        dist.all_reduce(colsum)
+    graph.norm_g = torch.where(deg > 0, deg / colsum.clamp(min=1e-30), torch.zeros_like(deg)).float()
+    graph.mean_g = (1.0 / (deg + 1)).float()
+    return graph
+
+
+class AllReduceSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = x.contiguous().clone()
+        if is_dist():
+            dist.all_reduce(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        if is_dist():
+            dist.all_reduce(g)
+        return g
+
+
+class _GenePartial(torch.autograd.Function):
+    """Shard-local raw gene sums S_g^p = Σ_{c in shard} x_cg·h_c (no α, no normaliser)."""
+
+    @staticmethod
+    def forward(ctx, hc, graph: BipartiteGraph, algo):
+        out, _, _ = ops.spmm(graph.gene_csr, hc, algo=algo)
+        ctx.graph, ctx.algo = graph, algo
+        return out
+
+    @staticmethod
+    def backward(ctx, ds):
+        dhc = None
+        if ctx.needs_input_grad[0]:
+            dhc, _, _ = ops.spmm(ctx.graph.cell_csr, ds.contiguous(), algo=ctx.algo)
+        return dhc, None, None
+
+
+def sharded_forward(model: GNN, graph: BipartiteGraph, features: torch.Tensor) -> torch.Tensor:
+    """GNN.forward on this rank's shard: features = cat[gene rows (replicated); local cell rows]."""
+    g = graph.num_genes
+    a = model.alpha.reshape(-1)
+    h = features
+    for i, layer in enumerate(model.layers):
+        if model.dropout:
+            h = model.dropout(h)
+        hg, hc = h[:g], h[g:]
+        last = i == model.n_layers - 1
+        neigh_c = _CellAggregate.apply(hg, hc, model.alpha, graph, model.spmm_algo)
+        if last:
+            h = layer(neigh_c)
+        else:
+            s = AllReduceSum.apply(_GenePartial.apply(hc, graph, model.spmm_algo))
+            neigh_g = s * (graph.mean_g * graph.norm_g * a[:g])[:, None] + hg * (graph.mean_g * a[g])[:, None]
+            h = layer(torch.cat([neigh_g, neigh_c], dim=0))
+    return model.linear(h)
+
+
+def allreduce_grads(model: torch.nn.Module):
+    """One flattened all-reduce(sum) of every parameter gradient (≈1.4 MB at H=400)."""
+    if not is_dist():
+        return
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def broadcast_params(model: torch.nn.Module, src=0):
+    if not is_dist():
+        return
+    for p in model.parameters():
+        dist.broadcast(p.data, src)
