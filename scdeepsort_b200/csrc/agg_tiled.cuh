@@ -28,12 +28,14 @@
 // no per-chunk predicates: a 400-float row is 3 full float4 chunks per lane plus one scalar
 // chunk on lanes 0..15 (13 shared-memory wavefronts per edge, the minimum for 1600 B).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wsage {
 
-constexpr int kTiledStages = 4;
-constexpr int kTiledSmemBudget = 200 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
+constexpr int kTiledStages = 4;                // deepest window ring among the compiled shapes
+constexpr int kTiledSmemBudget = 216 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
 constexpr int kTiledNW = 12;                   // consumer warps per CTA
 constexpr int kTiledR = 4;                     // destination rows per warp
 
@@ -46,6 +48,8 @@ struct TiledParams {
     int64_t n_dst;
     int dim;
     int win_rows;             // W
+    int pitch;                // floats between consecutive rows of a stage: dim rounded up to 32 (128 B),
+                              // so every 512-byte warp load touches exactly 4 shared-memory lines
     int n_windows;            // ceil(n_src / W)
     int n_tiles;
     int n_splits;
@@ -157,13 +161,14 @@ __device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t
     }
 }
 
-template <typename ColT, int DIM, int NW, int R>
+template <typename ColT, int DIM, int NW, int R, int STG>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 agg_tiled_kernel(const TiledParams p) {
     using S = RowShape<DIM>;
+    constexpr int kTiledStages = STG;       // depth of the window ring
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kTiledStages];
-    __shared__ uint64_t empty_bar[kTiledStages];
+    __shared__ uint64_t full_bar[STG];
+    __shared__ uint64_t empty_bar[STG];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -172,7 +177,8 @@ agg_tiled_kernel(const TiledParams p) {
     const int w_begin = split * p.win_per_split;
     const int w_end = min(p.n_windows, w_begin + p.win_per_split);
     const int dim = DIM > 0 ? DIM : p.dim;
-    const size_t stage_floats = (size_t)p.win_rows * dim;
+    const int pitch = DIM > 0 ? ((DIM + 31) & ~31) : p.pitch;
+    const size_t stage_floats = (size_t)p.win_rows * pitch;
     float* stages = reinterpret_cast<float*>(smem_raw);
 
     if (threadIdx.x == 0) {
@@ -187,17 +193,18 @@ agg_tiled_kernel(const TiledParams p) {
 
     if (warp == NW) {
         // ------------------------------- producer -------------------------------------------
-        if (lane == 0) {
-            for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
-                const int s = it % kTiledStages;
-                const uint32_t ph = (it / kTiledStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int64_t row0 = (int64_t)w * p.win_rows;
-                const int64_t rows = min((int64_t)p.win_rows, p.n_src - row0);
-                const uint32_t bytes = (uint32_t)(rows * dim * sizeof(float));
-                mbar_arrive_expect_tx(&full_bar[s], bytes);
-                bulk_g2s(stages + s * stage_floats, p.hs + row0 * dim, bytes, &full_bar[s]);
-            }
+        // one bulk copy per source row (lane l copies rows l, l+32, ...) into the padded stage
+        for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
+            const int s = it % kTiledStages;
+            const uint32_t ph = (it / kTiledStages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int64_t row0 = (int64_t)w * p.win_rows;
+            const int rows = (int)min((int64_t)p.win_rows, p.n_src - row0);
+            const uint32_t row_bytes = (uint32_t)(dim * sizeof(float));
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes);
+            __syncwarp();
+            for (int r = lane; r < rows; r += 32)
+                bulk_g2s(stages + s * stage_floats + (size_t)r * pitch, p.hs + (row0 + r) * dim, row_bytes, &full_bar[s]);
         }
         return;
     }
@@ -264,7 +271,7 @@ agg_tiled_kernel(const TiledParams p) {
         const uint32_t ph = (it / kTiledStages) & 1;
         const int win_base = w * p.win_rows;
         const int win_end = win_base + p.win_rows;
-        const float* stage = stages + s * stage_floats + lane * 4 - (size_t)win_base * dim;
+        const float* stage = stages + s * stage_floats + lane * 4 - (size_t)win_base * pitch;
         mbar_wait(&full_bar[s], ph);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -272,14 +279,14 @@ agg_tiled_kernel(const TiledParams p) {
                 const int l0 = cur[r] & 31;
                 const unsigned m = __ballot_sync(0xffffffffu, lane >= l0 && ccol[r] < win_end);
                 const int cnt = __popc(m);         // columns ascend: a contiguous run starting at lane l0
-                for (int k = 0; k < cnt; k += 2) {
+                int k = 0;
+                for (; k + 1 < cnt; k += 2) {          // two edges per iteration: 2x the loads in flight
                     const int c0 = __shfl_sync(0xffffffffu, ccol[r], l0 + k);
                     const float x0 = __shfl_sync(0xffffffffu, cx[r], l0 + k);
-                    int c1 = __shfl_sync(0xffffffffu, ccol[r], (l0 + k + 1) & 31);
-                    float x1 = __shfl_sync(0xffffffffu, cx[r], (l0 + k + 1) & 31);
-                    if (k + 1 >= cnt) { c1 = c0; x1 = 0.f; }       // odd tail: re-read edge 0 with weight 0
-                    const float* s0 = stage + (size_t)c0 * dim;
-                    const float* s1 = stage + (size_t)c1 * dim;
+                    const int c1 = __shfl_sync(0xffffffffu, ccol[r], l0 + k + 1);
+                    const float x1 = __shfl_sync(0xffffffffu, cx[r], l0 + k + 1);
+                    const float* s0 = stage + (size_t)c0 * pitch;
+                    const float* s1 = stage + (size_t)c1 * pitch;
                     float4 a4[S::N4], b4[S::N4];
                     float a1 = 0.f, b1 = 0.f;
 #pragma unroll
@@ -301,6 +308,21 @@ agg_tiled_kernel(const TiledParams p) {
                         }
                     }
                     if (S::TAIL1) acc[r].v1 = fmaf(x1, b1, fmaf(x0, a1, acc[r].v1));
+                }
+                if (k < cnt) {                           // odd edge left over
+                    const int c0 = __shfl_sync(0xffffffffu, ccol[r], l0 + k);
+                    const float x0 = __shfl_sync(0xffffffffu, cx[r], l0 + k);
+                    const float* s0 = stage + (size_t)c0 * pitch;
+                    float4 a4[S::N4];
+                    float a1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < S::N4; ++j)
+                        if (S::on4(j, lane, dim)) a4[j] = *reinterpret_cast<const float4*>(s0 + j * 128);
+                    if (S::TAIL1 && S::on1(lane)) a1 = s0[S::J4 * 128 - lane * 3];
+#pragma unroll
+                    for (int j = 0; j < S::N4; ++j)
+                        if (S::on4(j, lane, dim)) Vec<4>::fma(acc[r].v4[j], x0, a4[j]);
+                    if (S::TAIL1) acc[r].v1 = fmaf(x0, a1, acc[r].v1);
                 }
                 cur[r] += cnt;
                 if (cnt == 0 || (cur[r] & 31) != 0) break;
@@ -356,21 +378,43 @@ tiled_reduce_kernel(const TiledParams p) {
 }
 
 // ------------------------------------------ host side ------------------------------------------
+// Kernel shape: consumer warps per CTA, destination rows per warp, depth of the window ring.
+// WSAGE_TILED_VARIANT (env, tuning only) selects among the compiled shapes for dim == 400.
+struct TiledVariant { int nw, r, stages; };
+constexpr TiledVariant kTiledVariants[] = {{12, 4, 3}, {16, 3, 4}, {12, 4, 4}, {12, 4, 2}, {8, 6, 4}, {24, 2, 4}};   // [0] = default (best of the r01 sweep, profiles/r01_tiled_variants.md)
+constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
+
+inline int tiled_variant_index() {
+    static const int v = [] {
+        const char* e = getenv("WSAGE_TILED_VARIANT");
+        const int i = e ? atoi(e) : 0;
+        return (i >= 0 && i < kNumTiledVariants) ? i : 0;
+    }();
+    return v;
+}
+inline TiledVariant tiled_variant(const wsage_spmm_args* a) {
+    return kTiledVariants[a->dim == 400 ? tiled_variant_index() : 0];
+}
+
 struct TiledPlan {
-    int win_rows, n_windows, n_tiles, n_splits, win_per_split;
+    TiledVariant v;
+    int win_rows, pitch, n_windows, n_tiles, n_splits, win_per_split;
     size_t smem_bytes, workspace_bytes;
 };
 
 inline bool tiled_supported(const wsage_spmm_args* a, bool vec4) {
     return vec4 && a->dim <= 512 && a->ld_hs == a->dim && a->n_src < (int64_t)0x7fffffff &&
-           a->n_dst < (int64_t)0x7fffffff && (int64_t)a->dim * 4 * 8 <= kTiledSmemBudget / kTiledStages;
+           a->n_dst < (int64_t)0x7fffffff && (int64_t)((a->dim + 31) & ~31) * 4 * 8 <= kTiledSmemBudget / kTiledStages;
 }
 
 inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
     TiledPlan pl{};
-    const int rows_per_tile = kTiledNW * kTiledR;
+    pl.v = tiled_variant(a);
+    const int rows_per_tile = pl.v.nw * pl.v.r;
     const size_t row_bytes = (size_t)a->dim * sizeof(float);
-    int w = (int)(kTiledSmemBudget / kTiledStages / row_bytes);
+    pl.pitch = (a->dim + 31) & ~31;
+    const size_t pitch_bytes = (size_t)pl.pitch * sizeof(float);
+    int w = (int)(kTiledSmemBudget / pl.v.stages / pitch_bytes);
     if ((int64_t)w > a->n_src) w = (int)(a->n_src > 0 ? a->n_src : 1);
     pl.win_rows = w;
     pl.n_windows = (int)((a->n_src + w - 1) / w);
@@ -378,16 +422,19 @@ inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
     // (a) each split's slice of hs should stay L2-resident while the resident CTAs stream it
     const double table_bytes = (double)a->n_src * row_bytes;
     int splits = (int)((table_bytes + 40.0 * (1 << 20) - 1) / (40.0 * (1 << 20)));
-    // (b) >= ~48 waves of work units so the heaviest tile (degree-sorted, skewed) cannot dominate
-    const int balance = (48 * kNumSMs + pl.n_tiles - 1) / pl.n_tiles;
-    if (balance > splits) splits = balance;
+    // (b) few tiles means few, long, degree-skewed rows (gene destinations): cut them into >= ~48
+    //     waves of work units so the heaviest tile cannot dominate; many tiles balance by themselves
+    if (pl.n_tiles < 8 * kNumSMs) {
+        const int balance = (48 * kNumSMs + pl.n_tiles - 1) / pl.n_tiles;
+        if (balance > splits) splits = balance;
+    }
     const int max_splits = pl.n_windows / 8 > 0 ? pl.n_windows / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits > 256) splits = 256;
     if (splits < 1) splits = 1;
     pl.win_per_split = (pl.n_windows + splits - 1) / splits;
     pl.n_splits = (pl.n_windows + pl.win_per_split - 1) / pl.win_per_split;
-    pl.smem_bytes = (size_t)kTiledStages * w * row_bytes;
+    pl.smem_bytes = (size_t)pl.v.stages * w * pitch_bytes;
     pl.workspace_bytes = pl.n_splits > 1 ? (size_t)pl.n_splits * a->n_dst * a->dim * sizeof(float) : 0;
     return pl;
 }
@@ -402,26 +449,27 @@ inline size_t tiled_workspace_bytes(const wsage_spmm_args* a, bool vec4) {
 // work to amortise the pipeline; otherwise the L2 gather kernel wins.
 inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
     if (!tiled_supported(a, vec4) || a->n_src == 0 || a->n_dst == 0) return false;
+    const TiledVariant v = tiled_variant(a);
     const double avg_deg = (double)a->nnz / (double)a->n_dst;
-    const double reuse = avg_deg * kTiledNW * kTiledR / (double)a->n_src;
+    const double reuse = avg_deg * v.nw * v.r / (double)a->n_src;
     return reuse >= 1.5 && a->nnz >= (int64_t)1 << 20;
 }
 
-template <typename ColT, int DIM>
-int launch_tiled_dim(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
+template <typename ColT, int DIM, int NW, int R, int STG>
+int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
     TiledParams p{};
     p.rowptr = a->rowptr; p.col = a->col; p.x = a->x; p.hs = a->hs;
     p.n_src = a->n_src; p.n_dst = a->n_dst; p.dim = a->dim;
-    p.win_rows = pl.win_rows; p.n_windows = pl.n_windows; p.n_tiles = pl.n_tiles;
+    p.win_rows = pl.win_rows; p.pitch = pl.pitch; p.n_windows = pl.n_windows; p.n_tiles = pl.n_tiles;
     p.n_splits = pl.n_splits; p.win_per_split = pl.win_per_split; p.row_perm = a->row_perm;
     p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
     p.partial = static_cast<float*>(a->workspace);
-    auto kern = agg_tiled_kernel<ColT, DIM, kTiledNW, kTiledR>;
+    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_tiled)", cudaGetErrorString(e));
-    kern<<<pl.n_tiles * pl.n_splits, (kTiledNW + 1) * 32, pl.smem_bytes, st>>>(p);
+    kern<<<pl.n_tiles * pl.n_splits, (NW + 1) * 32, pl.smem_bytes, st>>>(p);
     int rc = check_launch("agg_tiled");
     if (rc != WSAGE_OK || pl.n_splits == 1) return rc;
     tiled_reduce_kernel<<<gather_grid(a->n_dst), 256, 0, st>>>(p);
@@ -431,10 +479,18 @@ int launch_tiled_dim(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t
 template <typename ColT>
 int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
     switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and the bench (400/400)
-        case 400: return launch_tiled_dim<ColT, 400>(a, pl, st);
-        case 200: return launch_tiled_dim<ColT, 200>(a, pl, st);
-        case 128: return launch_tiled_dim<ColT, 128>(a, pl, st);
-        default:  return launch_tiled_dim<ColT, 0>(a, pl, st);
+        case 400:
+            switch (tiled_variant_index()) {
+                case 1: return launch_tiled_shape<ColT, 400, 16, 3, 4>(a, pl, st);
+                case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4>(a, pl, st);
+                case 3: return launch_tiled_shape<ColT, 400, 12, 4, 2>(a, pl, st);
+                case 4: return launch_tiled_shape<ColT, 400, 8, 6, 4>(a, pl, st);
+                case 5: return launch_tiled_shape<ColT, 400, 24, 2, 4>(a, pl, st);
+                default: return launch_tiled_shape<ColT, 400, 12, 4, 3>(a, pl, st);
+            }
+        case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3>(a, pl, st);
+        case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3>(a, pl, st);
+        default:  return launch_tiled_shape<ColT, 0, 12, 4, 3>(a, pl, st);
     }
 }
 
