@@ -204,12 +204,14 @@ def run_ours(a):
     ops.TIMING = []
     sd._lib.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly the timed region
     e0.record()
     loss = None
     for _ in range(a.steps):
         loss = trainer.step(feats, labels, return_loss=False)
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / a.steps)
     launches = sd._lib.launch_count()
     timing, ops.TIMING = ops.TIMING, None
@@ -238,8 +240,12 @@ def run_ours(a):
                 "algorithmic_gbs": g["bytes"] / g["ms"] / 1e6, "gather_side_tbs": g["gather_bytes"] / g["ms"] / 1e9}
         key, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
         achieved = g["bytes"] / g["ms"] / 1e6
+        traffic = None          # ncu dram bytes per launch, recorded under profiles/ for the c4 shape
+        tj = ROOT / "profiles" / "r01_traffic.json"
+        if tj.exists() and (a.cells, a.genes, int(a.deg), a.dim, world) == (760_000, 20_000, 2000, 400, 1):
+            traffic = json.loads(tj.read_text())["c4"].get(f"{key[0]}:{key[1]}")
         roofline = {"kernel": f"agg_{key[0]} ({key[1]})", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "ms_per_launch": g["ms"] / g["n"],
                     "gather_side_tbs": g["gather_bytes"] / g["ms"] / 1e9,
                     "note": "algorithmic bytes count distinct rows once (SURVEY 8d); the E*D gather is served "
