@@ -162,6 +162,8 @@ __device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t
 }
 
 template <typename ColT, int DIM, int NW, int R, int STG>
+// one CTA per SM; ptxas derives the register cap from the warp count (16K registers per SM sub-partition,
+// so 13 warps -> 128 registers/thread, 12 warps -> 168)
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 agg_tiled_kernel(const TiledParams p) {
     using S = RowShape<DIM>;
@@ -381,7 +383,8 @@ tiled_reduce_kernel(const TiledParams p) {
 // Kernel shape: consumer warps per CTA, destination rows per warp, depth of the window ring.
 // WSAGE_TILED_VARIANT (env, tuning only) selects among the compiled shapes for dim == 400.
 struct TiledVariant { int nw, r, stages; };
-constexpr TiledVariant kTiledVariants[] = {{12, 4, 3}, {16, 3, 4}, {12, 4, 4}, {12, 4, 2}, {8, 6, 4}, {24, 2, 4}};   // [0] = default (best of the r01 sweep, profiles/r01_tiled_variants.md)
+// [0] = default (best of the round-1 sweeps, profiles/r01_summary.md)
+constexpr TiledVariant kTiledVariants[] = {{12, 4, 3}, {12, 4, 4}, {11, 4, 4}, {16, 3, 4}};
 constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
 
 inline int tiled_variant_index() {
@@ -481,11 +484,9 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t
     switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and the bench (400/400)
         case 400:
             switch (tiled_variant_index()) {
-                case 1: return launch_tiled_shape<ColT, 400, 16, 3, 4>(a, pl, st);
-                case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4>(a, pl, st);
-                case 3: return launch_tiled_shape<ColT, 400, 12, 4, 2>(a, pl, st);
-                case 4: return launch_tiled_shape<ColT, 400, 8, 6, 4>(a, pl, st);
-                case 5: return launch_tiled_shape<ColT, 400, 24, 2, 4>(a, pl, st);
+                case 1: return launch_tiled_shape<ColT, 400, 12, 4, 4>(a, pl, st);
+                case 2: return launch_tiled_shape<ColT, 400, 11, 4, 4>(a, pl, st);
+                case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4>(a, pl, st);
                 default: return launch_tiled_shape<ColT, 400, 12, 4, 3>(a, pl, st);
             }
         case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3>(a, pl, st);
