@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import dense, ops
 from .graph import BipartiteGraph
 from .nodeflow import FullGraphFlow, NodeFlow
 from .ops import Csr
@@ -31,10 +31,18 @@ class NodeUpdate(nn.Module):
         self.norm = norm
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=nn.init.calculate_gain('relu'))
 
+    use_tensor_cores = True     # tcgen05 kernel (bf16x3 split, fp32-grade accuracy) when the shape allows
+
     def forward(self, h_neigh):
-        h_neigh = self.fc_neigh(h_neigh)
-        if self.activation is not None:
-            h_neigh = self.activation(h_neigh)
+        fc = self.fc_neigh
+        relu = self.activation in (F.relu, torch.relu)
+        if (self.use_tensor_cores and h_neigh.is_cuda and (relu or self.activation is None)
+                and dense.tc_supported(fc.in_features, fc.out_features)):
+            h_neigh = dense.linear_relu(h_neigh, fc.weight, fc.bias, relu=relu)     # Linear + bias + ReLU fused
+        else:
+            h_neigh = fc(h_neigh)
+            if self.activation is not None:
+                h_neigh = self.activation(h_neigh)
         if self.norm is not None:
             h_neigh = self.norm(h_neigh)
         return h_neigh
@@ -145,7 +153,14 @@ class GNN(nn.Module):
             neigh = ops.block_aggregate(h, self.alpha, nf.blocks[i], nf.layers[i].data["id"].reshape(-1),
                                         nf.layers[i + 1].data["id"].reshape(-1), self.gene_num)
             h = layer(neigh)
-        return self.linear(h)
+        return self._classify(h)
+
+    def _classify(self, h):
+        """Final linear (models/gnn.py:67), on the tensor-core kernel when the shape allows."""
+        fc = self.linear
+        if NodeUpdate.use_tensor_cores and h.is_cuda and dense.tc_supported(fc.in_features, fc.out_features):
+            return dense.linear_relu(h, fc.weight, fc.bias, relu=False)
+        return fc(h)
 
     # -- throughput path: whole bipartite graph, layer by layer ----------------------------
     def _forward_full(self, flow: FullGraphFlow):
@@ -165,7 +180,7 @@ class GNN(nn.Module):
             else:
                 neigh_g = _GeneAggregate.apply(hg, hc[:ns], self.alpha, graph, self.spmm_algo)
                 h = layer(torch.cat([neigh_g, neigh_c], dim=0))
-        return self.linear(h)
+        return self._classify(h)
 
     def forward(self, nf):
         if not self.alpha.is_cuda:

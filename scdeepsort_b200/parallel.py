@@ -104,7 +104,7 @@ def sharded_forward(model: GNN, graph: BipartiteGraph, features: torch.Tensor) -
             s = AllReduceSum.apply(_GenePartial.apply(hc, graph, model.spmm_algo))
             neigh_g = s * (graph.mean_g * graph.norm_g * a[:g])[:, None] + hg * (graph.mean_g * a[g])[:, None]
             h = layer(torch.cat([neigh_g, neigh_c], dim=0))
-    return model.linear(h)
+    return model._classify(h)
 
 
 def allreduce_grads(model: torch.nn.Module):

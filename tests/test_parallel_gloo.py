@@ -64,6 +64,7 @@ def _full_reference():
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         sd.ops.spmm = _spmm_cpu
@@ -104,7 +105,7 @@ def test_two_rank_sharded_step_matches_single_process():
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
-    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     bg, feats, logits_full, loss_full, grads_full = _full_reference()
