@@ -130,22 +130,23 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
 /* ---------------------------------------------------------------------------------------
  * Post-aggregate dense layer on the tensor cores (tcgen05 / TMEM / TMA).
  *
- * Replaces NodeUpdate.forward (/root/reference/models/gnn.py:18-25: fc_neigh Linear + activation)
- * and the input-gradient GEMM of its backward.  fp32 accuracy is kept by splitting every operand
- * into bf16 hi + bf16 lo (wsage_split_bf16) and accumulating hi*hi + lo*hi + hi*lo in fp32.
+ * Replaces NodeUpdate.forward (/root/reference/models/gnn.py:18-25: fc_neigh Linear + activation),
+ * the classifier (models/gnn.py:67) and the input-gradient GEMM of their backward.  fp32 accuracy
+ * is kept by splitting every operand into tf32 hi + tf32 lo (wsage_split_tf32) and accumulating
+ * hi*hi + lo*hi + hi*lo in fp32 (residual ~2^-21 per product).
  *
- * wsage_split_bf16:  hi = bf16(v), lo = bf16(v - hi) with v = x, or v = x * (mask_src > 0) when
- *   mask_src is given (ReLU backward, models/gnn.py:22); `masked` (optional) receives v in fp32.
- *   cols % 4 == 0; all row pitches in elements.
- * wsage_linear_tc:   out[M,N] = act(A[M,K] * B[N,K]^T + bias), A/B given as bf16 hi/lo pairs with
- *   row pitches ld_a / ld_b (elements, multiples of 8), N <= 512 (computed on N rounded up to 16;
- *   the extra rows of B are zero-filled by TMA); relu != 0 applies max(.,0); bias may be NULL.
+ * wsage_split_tf32:  hi = rn_tf32(v), lo = rn_tf32(v - hi), stored as fp32, with v = x, or
+ *   v = x * (mask_src > 0) when mask_src is given (ReLU backward, models/gnn.py:22); `masked`
+ *   (optional) receives v in fp32.  cols % 4 == 0; all row pitches in elements, multiples of 4.
+ * wsage_linear_tc:   out[M,N] = act(A[M,K] * B[N,K]^T + bias), A/B given as hi/lo pairs with row
+ *   pitches ld_a / ld_b, N <= 512 (computed on N rounded up to 16; the extra rows of B are
+ *   zero-filled by TMA); relu != 0 applies max(.,0); bias may be NULL.
  * ------------------------------------------------------------------------------------- */
-int wsage_split_bf16(const float* x, int64_t ld_x, const float* mask_src, int64_t ld_mask,
-                     void* hi, void* lo, int64_t ld_out, float* masked, int64_t ld_masked,
+int wsage_split_tf32(const float* x, int64_t ld_x, const float* mask_src, int64_t ld_mask,
+                     float* hi, float* lo, int64_t ld_out, float* masked, int64_t ld_masked,
                      int64_t rows, int32_t cols, void* stream);
-int wsage_linear_tc(const void* a_hi, const void* a_lo, int64_t ld_a,
-                    const void* b_hi, const void* b_lo, int64_t ld_b,
+int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
+                    const float* b_hi, const float* b_lo, int64_t ld_b,
                     const float* bias, int32_t relu, float* out, int64_t ld_out,
                     int64_t m, int32_t n, int32_t k, void* stream);
 

@@ -18,7 +18,7 @@ ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
            "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm",
-           "wsage_split_bf16", "wsage_linear_tc")
+           "wsage_split_tf32", "wsage_linear_tc")
 
 
 class SpmmArgs(Structure):
@@ -73,8 +73,8 @@ def load():
     lib.wsage_spmm_algo.argtypes = [POINTER(SpmmArgs)]
     lib.wsage_spmm.restype = c_int32
     lib.wsage_spmm.argtypes = [POINTER(SpmmArgs), c_void_p]
-    lib.wsage_split_bf16.restype = c_int32
-    lib.wsage_split_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+    lib.wsage_split_tf32.restype = c_int32
+    lib.wsage_split_tf32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                      c_void_p, c_int64, c_int64, c_int32, c_void_p]
     lib.wsage_linear_tc.restype = c_int32
     lib.wsage_linear_tc.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int32,

@@ -35,7 +35,7 @@
 namespace wsage {
 
 constexpr int kTiledStages = 4;                // deepest window ring among the compiled shapes
-constexpr int kTiledSmemBudget = 216 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
+constexpr int kTiledSmemBudget = 224 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
 constexpr int kTiledNW = 12;                   // consumer warps per CTA
 constexpr int kTiledR = 4;                     // destination rows per warp
 
@@ -161,7 +161,7 @@ __device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t
     }
 }
 
-template <typename ColT, int DIM, int NW, int R, int STG>
+template <typename ColT, int DIM, int NW, int R, int STG, bool ESM>
 // one CTA per SM; ptxas derives the register cap from the warp count (16K registers per SM sub-partition,
 // so 13 warps -> 128 registers/thread, 12 warps -> 168)
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
@@ -182,6 +182,10 @@ agg_tiled_kernel(const TiledParams p) {
     const int pitch = DIM > 0 ? ((DIM + 31) & ~31) : p.pitch;
     const size_t stage_floats = (size_t)p.win_rows * pitch;
     float* stages = reinterpret_cast<float*>(smem_raw);
+    // ESM: the current 32-edge chunk of every row is also kept in shared memory so that an edge's
+    // (column, value) pair is fetched with ONE broadcast LDS.64 instead of two SHFLs (both go
+    // through the same LSU data pipe that bounds this kernel)
+    int2* edge_buf = reinterpret_cast<int2*>(stages + (size_t)STG * stage_floats) + (size_t)(warp < NW ? warp : 0) * R * 32;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -262,10 +266,28 @@ agg_tiled_kernel(const TiledParams p) {
 #pragma unroll
         for (int r = 0; r < R; ++r) cur[r] = __shfl_sync(0xffffffffu, found, r);
     }
+    auto publish = [&](int r) {       // current chunk of row r -> shared memory (warp-private region)
+        if (ESM) {
+            __syncwarp();
+            edge_buf[r * 32 + lane] = make_int2(ccol[r], __float_as_int(cx[r]));
+            __syncwarp();
+        }
+    };
+    auto edge = [&](int r, int idx, int& c_out, float& x_out) {     // (column, value) of edge idx of the chunk
+        if (ESM) {
+            const int2 e = edge_buf[r * 32 + idx];
+            c_out = e.x;
+            x_out = __int_as_float(e.y);
+        } else {
+            c_out = __shfl_sync(0xffffffffu, ccol[r], idx);
+            x_out = __shfl_sync(0xffffffffu, cx[r], idx);
+        }
+    };
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         fetch(r, cur[r] & ~31, ccol[r], cx[r]);
         fetch(r, (cur[r] & ~31) + 32, ncol[r], nx[r]);
+        publish(r);
     }
 
     for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
@@ -283,10 +305,10 @@ agg_tiled_kernel(const TiledParams p) {
                 const int cnt = __popc(m);         // columns ascend: a contiguous run starting at lane l0
                 int k = 0;
                 for (; k + 1 < cnt; k += 2) {          // two edges per iteration: 2x the loads in flight
-                    const int c0 = __shfl_sync(0xffffffffu, ccol[r], l0 + k);
-                    const float x0 = __shfl_sync(0xffffffffu, cx[r], l0 + k);
-                    const int c1 = __shfl_sync(0xffffffffu, ccol[r], l0 + k + 1);
-                    const float x1 = __shfl_sync(0xffffffffu, cx[r], l0 + k + 1);
+                    int c0, c1;
+                    float x0, x1;
+                    edge(r, l0 + k, c0, x0);
+                    edge(r, l0 + k + 1, c1, x1);
                     const float* s0 = stage + (size_t)c0 * pitch;
                     const float* s1 = stage + (size_t)c1 * pitch;
                     float4 a4[S::N4], b4[S::N4];
@@ -312,8 +334,9 @@ agg_tiled_kernel(const TiledParams p) {
                     if (S::TAIL1) acc[r].v1 = fmaf(x1, b1, fmaf(x0, a1, acc[r].v1));
                 }
                 if (k < cnt) {                           // odd edge left over
-                    const int c0 = __shfl_sync(0xffffffffu, ccol[r], l0 + k);
-                    const float x0 = __shfl_sync(0xffffffffu, cx[r], l0 + k);
+                    int c0;
+                    float x0;
+                    edge(r, l0 + k, c0, x0);
                     const float* s0 = stage + (size_t)c0 * pitch;
                     float4 a4[S::N4];
                     float a1 = 0.f;
@@ -333,6 +356,7 @@ agg_tiled_kernel(const TiledParams p) {
                 ccol[r] = ncol[r];
                 cx[r] = nx[r];
                 fetch(r, cur[r] + 32, ncol[r], nx[r]);
+                publish(r);
             }
         }
         __syncwarp();
@@ -382,9 +406,9 @@ tiled_reduce_kernel(const TiledParams p) {
 // ------------------------------------------ host side ------------------------------------------
 // Kernel shape: consumer warps per CTA, destination rows per warp, depth of the window ring.
 // WSAGE_TILED_VARIANT (env, tuning only) selects among the compiled shapes for dim == 400.
-struct TiledVariant { int nw, r, stages; };
+struct TiledVariant { int nw, r, stages; bool esm; };
 // [0] = default (best of the round-1 sweeps, profiles/r01_summary.md)
-constexpr TiledVariant kTiledVariants[] = {{12, 4, 3}, {12, 4, 4}, {11, 4, 4}, {16, 3, 4}};
+constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}};
 constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
 
 inline int tiled_variant_index() {
@@ -417,7 +441,8 @@ inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
     const size_t row_bytes = (size_t)a->dim * sizeof(float);
     pl.pitch = (a->dim + 31) & ~31;
     const size_t pitch_bytes = (size_t)pl.pitch * sizeof(float);
-    int w = (int)(kTiledSmemBudget / pl.v.stages / pitch_bytes);
+    const size_t edge_bytes = pl.v.esm ? (size_t)pl.v.nw * pl.v.r * 32 * sizeof(int2) : 0;
+    int w = (int)((kTiledSmemBudget - edge_bytes) / pl.v.stages / pitch_bytes);
     if ((int64_t)w > a->n_src) w = (int)(a->n_src > 0 ? a->n_src : 1);
     pl.win_rows = w;
     pl.n_windows = (int)((a->n_src + w - 1) / w);
@@ -437,7 +462,7 @@ inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
     if (splits < 1) splits = 1;
     pl.win_per_split = (pl.n_windows + splits - 1) / splits;
     pl.n_splits = (pl.n_windows + pl.win_per_split - 1) / pl.win_per_split;
-    pl.smem_bytes = (size_t)pl.v.stages * w * pitch_bytes;
+    pl.smem_bytes = (size_t)pl.v.stages * w * pitch_bytes + (pl.v.esm ? (size_t)pl.v.nw * pl.v.r * 32 * sizeof(int2) : 0);
     pl.workspace_bytes = pl.n_splits > 1 ? (size_t)pl.n_splits * a->n_dst * a->dim * sizeof(float) : 0;
     return pl;
 }
@@ -458,7 +483,7 @@ inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
     return reuse >= 1.5 && a->nnz >= (int64_t)1 << 20;
 }
 
-template <typename ColT, int DIM, int NW, int R, int STG>
+template <typename ColT, int DIM, int NW, int R, int STG, bool ESM>
 int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
     TiledParams p{};
     p.rowptr = a->rowptr; p.col = a->col; p.x = a->x; p.hs = a->hs;
@@ -469,7 +494,7 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
     p.partial = static_cast<float*>(a->workspace);
-    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG>;
+    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG, ESM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_tiled)", cudaGetErrorString(e));
     kern<<<pl.n_tiles * pl.n_splits, (NW + 1) * 32, pl.smem_bytes, st>>>(p);
@@ -484,14 +509,14 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t
     switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and the bench (400/400)
         case 400:
             switch (tiled_variant_index()) {
-                case 1: return launch_tiled_shape<ColT, 400, 12, 4, 4>(a, pl, st);
-                case 2: return launch_tiled_shape<ColT, 400, 11, 4, 4>(a, pl, st);
-                case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4>(a, pl, st);
-                default: return launch_tiled_shape<ColT, 400, 12, 4, 3>(a, pl, st);
+                case 1: return launch_tiled_shape<ColT, 400, 12, 4, 3, false>(a, pl, st);
+                case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4, true>(a, pl, st);
+                case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, st);
+                default: return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, st);
             }
-        case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3>(a, pl, st);
-        case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3>(a, pl, st);
-        default:  return launch_tiled_shape<ColT, 0, 12, 4, 3>(a, pl, st);
+        case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3, true>(a, pl, st);
+        case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3, true>(a, pl, st);
+        default:  return launch_tiled_shape<ColT, 0, 12, 4, 3, true>(a, pl, st);
     }
 }
 

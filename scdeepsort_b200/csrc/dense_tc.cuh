@@ -4,36 +4,44 @@
 //
 // replaces NodeUpdate.forward (/root/reference/models/gnn.py:18-25: fc_neigh + activation) and its
 // input-gradient GEMM.  fp32 parity (1e-4) rules out plain bf16/tf32, so every operand is split into
-// bf16 hi + bf16 lo (split_bf16_kernel) and three MMAs are accumulated per k-step in TMEM:
-//   hi*hi + lo*hi + hi*lo   (dropped lo*lo term ~2^-16 relative per product).
+// tf32 hi + tf32 lo (split_tf32_kernel: hi = rn_tf32(x), lo = rn_tf32(x - hi), both stored as fp32
+// words whose low 13 bits are zero, so the tensor core reads them exactly) and three MMAs are
+// accumulated per k-step in TMEM:  hi*hi + lo*hi + hi*lo   (residual ~2^-21 relative per product,
+// i.e. fp32-grade; a bf16 split would leave ~2^-17).
 //
 // One CTA per 128-row tile (persistent, static stride), all N <= 512 columns in TMEM:
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SASS UTMALDG) of A_hi/A_lo [128 x 32] and
-//               B_hi/B_lo [N x 32] bf16 tiles, 64-byte swizzle, 3-stage mbarrier ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (SASS UTCHMMA), commits to the ring
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SASS UTMALDG) of A_hi/A_lo [128 x 16] and
+//               B_hi/B_lo [N x 16] tf32 tiles, 64-byte swizzle, 3-stage mbarrier ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer (SASS UTCHMMA), commits to the ring
 //   warps 2..5  epilogue: tcgen05.ld (LDTM) 32 lanes x 32 columns -> +bias, ReLU -> shared-memory
 //               transpose -> coalesced 128-byte global stores
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace wsage {
 
 constexpr int kTcBlockM = 128;
-constexpr int kTcBlockK = 32;          // bf16 elements per k-block = 64 bytes = one 64B-swizzle row
+constexpr int kTcBlockK = 16;          // tf32 elements per k-block = 64 bytes = one 64B-swizzle row
+constexpr int kTcUmmaK = 8;            // K of one tcgen05.mma.kind::tf32 (32 bytes)
 constexpr int kTcStages = 3;
 constexpr int kTcThreads = 192;        // 6 warps
 constexpr int kTcMaxN = 512;           // TMEM columns
 
 // ------------------------------------------------------------------------------------------------
-// fp32 -> (bf16 hi, bf16 lo) split, optionally fused with the ReLU-backward mask (g = x * (y > 0))
+// fp32 -> (tf32 hi, tf32 lo) split, optionally fused with the ReLU-backward mask (g = x * (y > 0))
 // and an fp32 copy of the masked value (for the weight-gradient GEMM).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rn_tf32(float v) {       // round to nearest tf32, returned as an fp32 word
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 __global__ void __launch_bounds__(256)
-split_bf16_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ mask_src, int64_t ld_m,
-                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_o,
+split_tf32_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ mask_src, int64_t ld_m,
+                  float* __restrict__ hi, float* __restrict__ lo, int64_t ld_o,
                   float* __restrict__ masked, int64_t ld_mk, int64_t rows, int cols) {
     const int64_t n4 = cols / 4;
     const int64_t total = rows * n4;
@@ -47,15 +55,11 @@ split_bf16_kernel(const float* __restrict__ x, int64_t ld_x, const float* __rest
             v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
             if (masked) *reinterpret_cast<float4*>(masked + r * ld_mk + c) = v;
         }
-        const float f[4] = {v.x, v.y, v.z, v.w};
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            h[k] = __float2bfloat16_rn(f[k]);
-            l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
-        }
-        *reinterpret_cast<uint2*>(hi + r * ld_o + c) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(lo + r * ld_o + c) = *reinterpret_cast<const uint2*>(l);
+        float4 h, l;
+        h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+        l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y); l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
+        *reinterpret_cast<float4*>(hi + r * ld_o + c) = h;
+        *reinterpret_cast<float4*>(lo + r * ld_o + c) = l;
     }
 }
 
@@ -71,12 +75,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {      // arrives on bar when all prior MMAs of this thread retire
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate; issued by ONE thread for the CTA.
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread for the CTA.
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major operand tile, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO), LBO unused (=1).
@@ -89,9 +93,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(const void* smem) {
     d |= (uint64_t)4 << 61;                                    // layout type SWIZZLE_64B
     return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+// kind::tf32 instruction descriptor: D fp32 (1), A/B tf32 (2), both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -122,8 +126,8 @@ struct LinearTcParams {
 };
 
 struct LinearTcSmem {       // carved from dynamic shared memory (1024-byte aligned)
-    static constexpr int a_bytes = kTcBlockM * kTcBlockK * 2;            // 8 KB per hi / lo tile
-    static __host__ __device__ int b_bytes(int n) { return n * kTcBlockK * 2; }
+    static constexpr int a_bytes = kTcBlockM * kTcBlockK * 4;            // 8 KB per hi / lo tile
+    static __host__ __device__ int b_bytes(int n) { return n * kTcBlockK * 4; }
     static __host__ __device__ int stage_bytes(int n) { return 2 * a_bytes + 2 * b_bytes(n); }
     static __host__ __device__ size_t total(int n) {
         return (size_t)kTcStages * stage_bytes(n) + 4 * 32 * 33 * sizeof(float) + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -186,8 +190,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     unsigned char* sb = st + 2 * LinearTcSmem::a_bytes;
                     for (int j = 0; j < p.b_boxes; ++j) {
                         const int r0 = j * p.b_box_rows;
-                        tma_load_2d(sb + r0 * kTcBlockK * 2, &map_b_hi, k0, r0, &full_bar[s]);
-                        tma_load_2d(sb + b_bytes + r0 * kTcBlockK * 2, &map_b_lo, k0, r0, &full_bar[s]);
+                        tma_load_2d(sb + r0 * kTcBlockK * 4, &map_b_hi, k0, r0, &full_bar[s]);
+                        tma_load_2d(sb + b_bytes + r0 * kTcBlockK * 4, &map_b_lo, k0, r0, &full_bar[s]);
                     }
                 }
             }
@@ -195,8 +199,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------ MMA issuer --------------------------------------
         if (lane == 0) {
-            const uint32_t idesc1 = umma_idesc_bf16(p.n1);
-            const uint32_t idesc2 = umma_idesc_bf16(p.n2 > 0 ? p.n2 : 16);
+            const uint32_t idesc1 = umma_idesc_tf32(p.n1);
+            const uint32_t idesc2 = umma_idesc_tf32(p.n2 > 0 ? p.n2 : 16);
             int it = 0, local_tile = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
                 mbar_wait(tmem_empty, (local_tile & 1) ^ 1);       // epilogue has drained the accumulators
@@ -210,19 +214,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     const uint64_t a_hi = umma_desc_sw64(st), a_lo = umma_desc_sw64(st + LinearTcSmem::a_bytes);
                     unsigned char* sb = st + 2 * LinearTcSmem::a_bytes;
                     const uint64_t b_hi = umma_desc_sw64(sb), b_lo = umma_desc_sw64(sb + b_bytes);
-                    const uint64_t n2_off = (uint64_t)((p.n1 * kTcBlockK * 2) >> 4);
+                    const uint64_t n2_off = (uint64_t)((p.n1 * kTcBlockK * 4) >> 4);
 #pragma unroll
-                    for (int kk = 0; kk < kTcBlockK / 16; ++kk) {      // UMMA_K = 16 bf16 = 32 bytes along K
+                    for (int kk = 0; kk < kTcBlockK / kTcUmmaK; ++kk) {      // UMMA_K = 8 tf32 = 32 bytes along K
                         const uint64_t ko = (uint64_t)(kk * 32 >> 4);
                         const uint32_t acc0 = (kb | kk) != 0;
                         // hi*hi, lo*hi, hi*lo  (smallest terms last does not matter: fp32 accumulate)
-                        tc_mma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
-                        tc_mma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
-                        tc_mma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                        tc_mma_tf32(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
+                        tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
+                        tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
                         if (p.n2 > 0) {
-                            tc_mma_bf16(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
-                            tc_mma_bf16(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
-                            tc_mma_bf16(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                            tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
+                            tc_mma_tf32(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
+                            tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
                         }
                     }
                     tc_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
@@ -291,15 +295,15 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// bf16 matrix [rows, cols] with row pitch ld (elements): box = [box_rows, 32 cols], 64-byte swizzle.
-inline int make_bf16_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// fp32 (tf32-valued) matrix [rows, cols] with row pitch ld (elements): box = [box_rows, 16 cols], 64-byte swizzle.
+inline int make_tf32_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(WSAGE_ECUDA, "%s: %s", "wsage_linear_tc", "cuTensorMapEncodeTiled not available");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     const cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(WSAGE_ECUDA, "%s: %s", "wsage_linear_tc", "cuTensorMapEncodeTiled failed");

@@ -118,8 +118,8 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream) {
                                         : launch_gather_fwd<int32_t, false>(p, vec4, st);
 }
 
-int wsage_split_bf16(const float* x, int64_t ld_x, const float* mask_src, int64_t ld_mask,
-                     void* hi, void* lo, int64_t ld_out, float* masked, int64_t ld_masked,
+int wsage_split_tf32(const float* x, int64_t ld_x, const float* mask_src, int64_t ld_mask,
+                     float* hi, float* lo, int64_t ld_out, float* masked, int64_t ld_masked,
                      int64_t rows, int32_t cols, void* stream) {
     WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     if (rows == 0) return WSAGE_OK;
@@ -127,19 +127,17 @@ int wsage_split_bf16(const float* x, int64_t ld_x, const float* mask_src, int64_
     WSAGE_REQUIRE(ld_x >= cols && ld_out >= cols && ld_x % 4 == 0 && ld_out % 4 == 0, "bad leading dimension");
     WSAGE_REQUIRE(!mask_src || (ld_mask >= cols && ld_mask % 4 == 0), "bad mask leading dimension");
     WSAGE_REQUIRE(!masked || (mask_src && ld_masked >= cols && ld_masked % 4 == 0), "masked output needs mask_src");
-    WSAGE_REQUIRE(aligned16(x) && aligned16(mask_src) && aligned16(masked) && ((uintptr_t)hi & 7) == 0 && ((uintptr_t)lo & 7) == 0,
-                  "misaligned pointer");
+    WSAGE_REQUIRE(aligned16(x) && aligned16(mask_src) && aligned16(masked) && aligned16(hi) && aligned16(lo), "misaligned pointer");
     const int64_t total = rows * (cols / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    split_bf16_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, ld_x, mask_src, ld_mask, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ld_out,
-        masked, ld_masked, rows, cols);
-    return check_launch("split_bf16");
+    split_tf32_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ld_x, mask_src, ld_mask, hi, lo, ld_out, masked, ld_masked, rows, cols);
+    return check_launch("split_tf32");
 }
 
-int wsage_linear_tc(const void* a_hi, const void* a_lo, int64_t ld_a,
-                    const void* b_hi, const void* b_lo, int64_t ld_b,
+int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
+                    const float* b_hi, const float* b_lo, int64_t ld_b,
                     const float* bias, int32_t relu, float* out, int64_t ld_out,
                     int64_t m, int32_t n, int32_t k, void* stream) {
     WSAGE_REQUIRE(m >= 0 && n > 0 && k > 0, "bad shape");
@@ -148,7 +146,7 @@ int wsage_linear_tc(const void* a_hi, const void* a_lo, int64_t ld_a,
     // the MMA computes n_pad = N rounded up to 16 columns; rows of B past N are zero-filled by TMA
     const int n_pad = (n + 15) & ~15;
     WSAGE_REQUIRE(n_pad <= kTcMaxN, "N must be <= 512");
-    WSAGE_REQUIRE(ld_a >= k && ld_b >= k && ld_a % 8 == 0 && ld_b % 8 == 0 && ld_out >= n, "bad leading dimension");
+    WSAGE_REQUIRE(ld_a >= k && ld_b >= k && ld_a % 4 == 0 && ld_b % 4 == 0 && ld_out >= n, "bad leading dimension");
     WSAGE_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo), "operands must be 16-byte aligned");
     WSAGE_REQUIRE(m < ((int64_t)1 << 31) - kTcBlockM, "M too large");
     LinearTcParams p{};
@@ -164,10 +162,10 @@ int wsage_linear_tc(const void* a_hi, const void* a_lo, int64_t ld_a,
         return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_linear_tc", "N too large for the 3-stage shared-memory ring");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_bf16_map(&ma_hi, a_hi, m, k, ld_a, kTcBlockM)) != WSAGE_OK) return rc;
-    if ((rc = make_bf16_map(&ma_lo, a_lo, m, k, ld_a, kTcBlockM)) != WSAGE_OK) return rc;
-    if ((rc = make_bf16_map(&mb_hi, b_hi, n, k, ld_b, p.b_box_rows)) != WSAGE_OK) return rc;
-    if ((rc = make_bf16_map(&mb_lo, b_lo, n, k, ld_b, p.b_box_rows)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_map(&ma_hi, a_hi, m, k, ld_a, kTcBlockM)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_map(&ma_lo, a_lo, m, k, ld_a, kTcBlockM)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_map(&mb_hi, b_hi, n, k, ld_b, p.b_box_rows)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_map(&mb_lo, b_lo, n, k, ld_b, p.b_box_rows)) != WSAGE_OK) return rc;
     cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(linear_tc)", cudaGetErrorString(e));
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;

@@ -176,8 +176,8 @@ def test_synthetic_golden_both_paths(golden_syn, tag, n_layers):
         a = model(nf).cpu()
         bg = sd.BipartiteGraph.from_expression(z[f"{tag}/x"], device=DEV)
         b = model(sd.FullGraphFlow(bg, gg.features.to(DEV))).cpu()
-    assert rel_err(a, z[f"{tag}/L{n_layers}/logits"]) < 5e-5      # bf16x3 tensor-core linear: ~2e-5 at K=4, <1e-5 at K>=40
-    assert rel_err(b, z[f"{tag}/L{n_layers}/logits"]) < 5e-5
+    assert rel_err(a, z[f"{tag}/L{n_layers}/logits"]) < 1e-5
+    assert rel_err(b, z[f"{tag}/L{n_layers}/logits"]) < 1e-5
 
 
 @pytest.mark.parametrize("n_src,dim,algo", [(300, 64, 1), (70000, 32, 1), (300, 18, 1), (300, 400, 0), (300, 400, 2), (5000, 128, 2)])

@@ -84,8 +84,9 @@ def _worker(rank, world, port, q):
         x = torch.full((3,), float(rank + 1), requires_grad=True)
         y = parallel.AllReduceSum.apply(x)
         (y * (rank + 1)).sum().backward()
-        q.put((rank, lo, hi, bg.norm_g.clone(), bg.mean_g.clone(), logits.detach(), float(total),
-               {k: p.grad.clone() for k, p in m.named_parameters()}, y.detach(), x.grad.clone()))
+        # numpy, not tensors: tensors travel through the queue as shared-memory fds, which die with this process
+        q.put((rank, lo, hi, bg.norm_g.numpy(), bg.mean_g.numpy(), logits.detach().numpy(), float(total),
+               {k: p.grad.numpy() for k, p in m.named_parameters()}, y.detach().numpy(), x.grad.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -109,14 +110,17 @@ def test_two_rank_sharded_step_matches_single_process():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     bg, feats, logits_full, loss_full, grads_full = _full_reference()
+    t = torch.from_numpy
     for rank, lo, hi, norm_g, mean_g, logits, total, grads, y, xg in res:
+        norm_g, mean_g, logits, y, xg = t(norm_g), t(mean_g), t(logits), t(y), t(xg)
+        grads = {k: t(v) for k, v in grads.items()}
         assert torch.allclose(norm_g, bg.norm_g, rtol=1e-6) and torch.allclose(mean_g, bg.mean_g)
         assert torch.allclose(logits, logits_full[lo:hi], rtol=1e-4, atol=1e-5)
         assert abs(total - loss_full) < 1e-4 * abs(loss_full)
         for k, g in grads_full.items():
             assert torch.allclose(grads[k], g, rtol=2e-4, atol=1e-5), k
         assert torch.equal(y, torch.full((3,), 3.0)) and torch.equal(xg, torch.full((3,), 3.0))
-    assert torch.equal(res[0][7]["alpha"], res[1][7]["alpha"])          # identical after the all-reduce
+    assert np.array_equal(res[0][7]["alpha"], res[1][7]["alpha"])        # identical after the all-reduce
 
 
 def test_sharded_math_matches_oracle():
