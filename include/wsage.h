@@ -150,6 +150,18 @@ int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
                     const float* bias, int32_t relu, float* out, int64_t ld_out,
                     int64_t m, int32_t n, int32_t k, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * GPU neighbour sampler.  Replaces dgl.contrib.sampling.NeighborSampler's per-hop draw
+ * (/root/reference/train.py:71-78: expand_factor in-edges per node, uniform, without
+ * replacement; DGL 0.4.3 _CAPI_UniformSampling on the host).  rowptr is the parent graph's
+ * in-edge CSR row pointer; for destination node nodes[i] the chosen edge positions (absolute
+ * indices into the CSR arrays, ascending) are written to out_eid[i*fanout .. i*fanout+out_deg[i])
+ * with out_deg[i] = min(in-degree, fanout).  1 <= fanout <= 32.  Same (seed, node) -> same draw.
+ * ------------------------------------------------------------------------------------- */
+int wsage_sample_neighbors(const int64_t* rowptr, const int64_t* nodes, int64_t n_nodes,
+                           int32_t fanout, uint64_t seed, int64_t* out_eid, int32_t* out_deg,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

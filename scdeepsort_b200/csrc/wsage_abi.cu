@@ -2,6 +2,7 @@
 #include "agg_gather.cuh"
 #include "agg_tiled.cuh"
 #include "dense_tc.cuh"
+#include "sampler.cuh"
 
 using namespace wsage;
 
@@ -171,6 +172,18 @@ int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     linear_tc_kernel<<<grid, kTcThreads, smem, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     return check_launch("linear_tc");
+}
+
+int wsage_sample_neighbors(const int64_t* rowptr, const int64_t* nodes, int64_t n_nodes,
+                           int32_t fanout, uint64_t seed, int64_t* out_eid, int32_t* out_deg,
+                           void* stream) {
+    WSAGE_REQUIRE(n_nodes >= 0, "negative n_nodes");
+    WSAGE_REQUIRE(fanout >= 1 && fanout <= kSampleMaxFanout, "fanout must be in [1, 32]");
+    if (n_nodes == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(rowptr && nodes && out_eid && out_deg, "null pointer");
+    sample_neighbors_kernel<<<gather_grid(n_nodes), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rowptr, nodes, n_nodes, fanout, seed, out_eid, out_deg);
+    return check_launch("sample_neighbors");
 }
 
 }  // extern "C"

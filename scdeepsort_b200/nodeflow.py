@@ -69,8 +69,28 @@ class NodeFlow:
         return nf
 
 
-def _in_edges(g: DeepSortGraph, nodes: torch.Tensor, fanout: Optional[int], gen: Optional[torch.Generator]):
+def _sample_edges_cuda(g: DeepSortGraph, nodes: torch.Tensor, fanout: int, seed: int):
+    """K6: wsage_sample_neighbors — warp-per-node Floyd sampling on the device (fanout <= 32)."""
+    import ctypes
+    from . import _lib
+    n = int(nodes.shape[0])
+    eid = torch.empty(n, fanout, dtype=torch.int64, device=nodes.device)
+    deg = torch.empty(n, dtype=torch.int32, device=nodes.device)
+    lib = _lib.load()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())      # noqa: E731
+    _lib.check(lib.wsage_sample_neighbors(p(g.in_rowptr), p(nodes), n, fanout, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                          p(eid), p(deg), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "wsage_sample_neighbors")
+    deg = deg.to(torch.int64)
+    keep = torch.arange(fanout, device=nodes.device)[None, :] < deg[:, None]
+    return eid[keep], deg                                # row-major: grouped by node, ascending inside a node
+
+
+def _in_edges(g: DeepSortGraph, nodes: torch.Tensor, fanout: Optional[int], gen: Optional[torch.Generator],
+              seed: Optional[int] = None):
     """Edge positions (into g.in_src) of the in-edges of ``nodes``, grouped by node in order."""
+    if fanout is not None and nodes.is_cuda and fanout <= 32 and nodes.shape[0] > 0:
+        return _sample_edges_cuda(g, nodes.contiguous(), fanout, seed if seed is not None else 0)
     start = g.in_rowptr[nodes]
     deg = g.in_rowptr[nodes + 1] - start
     total = int(deg.sum())
@@ -99,7 +119,7 @@ class NeighborSampler:
 
     def __init__(self, g: DeepSortGraph, batch_size, expand_factor=None, num_hops=1, neighbor_type='in',
                  transition_prob=None, seed_nodes=None, shuffle=False, num_workers=1, prefetch=False,
-                 add_self_loop=False, generator: Optional[torch.Generator] = None):
+                 add_self_loop=False, generator: Optional[torch.Generator] = None, fanouts=None, seed=10086):
         if neighbor_type != 'in':
             raise NotImplementedError("only in-neighbour sampling is on the hot path (train.py:75)")
         if transition_prob is not None or add_self_loop:
@@ -108,7 +128,13 @@ class NeighborSampler:
         self.batch_size = int(batch_size)
         self.num_hops = int(num_hops)
         max_deg = int((g.in_rowptr[1:] - g.in_rowptr[:-1]).max()) if g.number_of_nodes() else 0
-        self.fanout = None if expand_factor is None or int(expand_factor) >= max_deg else int(expand_factor)
+        clip = lambda f: None if f is None or int(f) >= max_deg else int(f)      # noqa: E731
+        # reference: ONE expand_factor for every hop (train.py:73); `fanouts` (seed hop first, e.g. [25, 10, 5])
+        # is the per-hop extension BASELINE.json's sampled configuration names
+        self.fanouts = [clip(expand_factor)] * self.num_hops if fanouts is None else [clip(f) for f in fanouts]
+        if len(self.fanouts) != self.num_hops:
+            raise ValueError("fanouts needs one entry per hop")
+        self.seed, self._batch = int(seed), 0
         if seed_nodes is None:
             seed_nodes = torch.arange(g.number_of_nodes())
         self.seed_nodes = torch.as_tensor(seed_nodes, dtype=torch.int64).reshape(-1).to(g.device)
@@ -124,9 +150,11 @@ class NeighborSampler:
         blocks = [None] * self.num_hops
         eids = [None] * self.num_hops
         layer_nid[self.num_hops] = seeds
+        self._batch += 1
         for hop in range(self.num_hops, 0, -1):
             dst_nodes = layer_nid[hop]
-            eid, deg = _in_edges(g, dst_nodes, self.fanout, self.generator)
+            eid, deg = _in_edges(g, dst_nodes, self.fanouts[self.num_hops - hop], self.generator,
+                                 seed=self.seed + 1000003 * self._batch + hop)
             src_parent = g.in_src[eid]
             src_nodes = torch.unique(src_parent)                   # sorted parent ids
             layer_nid[hop - 1] = src_nodes
