@@ -457,6 +457,10 @@ inline TiledPlan tiled_plan(const wsage_spmm_args* a) {
         if (balance > splits) splits = balance;
     }
     const int max_splits = pl.n_windows / 8 > 0 ? pl.n_windows / 8 : 1;
+    {   // WSAGE_TILED_SPLITS (env, tuning only) overrides the heuristic
+        static const int forced = [] { const char* e = getenv("WSAGE_TILED_SPLITS"); return e ? atoi(e) : 0; }();
+        if (forced > 0) splits = forced;
+    }
     if (splits > max_splits) splits = max_splits;
     if (splits > 256) splits = 256;
     if (splits < 1) splits = 1;
