@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--cpu-sample-cells", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="full", choices=["full", "sampled"],
+                    help="full = BASELINE metric (full-graph step); sampled = configs[4]: neighbour-sampled mini-batches")
+    ap.add_argument("--fanouts", default="25,10,5", help="sampled mode: per-hop fan-outs, seed hop first")
+    ap.add_argument("--batch", type=int, default=1024, help="sampled mode: seed cells per GPU per step")
     return ap.parse_args()
 
 
@@ -292,9 +296,91 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_sampled(a):
+    """BASELINE configs[4]: neighbour-sampled mini-batch training (graph replicated per GPU, seeds sharded,
+    gradients all-reduced).  Not the driver's default line; `python bench.py --mode sampled --layers 3 --hidden 800`."""
+    import torch.distributed as dist
+    import scdeepsort_b200 as sd
+    from scdeepsort_b200 import parallel
+    from scdeepsort_b200.synthetic import synthetic_bipartite, synthetic_features
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    fanouts = [int(f) for f in a.fanouts.split(",")]
+    if len(fanouts) != a.layers:
+        raise SystemExit("--fanouts needs one entry per layer")
+    t0 = time.time()
+    bg = synthetic_bipartite(a.cells, a.genes, a.deg, seed=SEED, device=dev)
+    feats = synthetic_features(bg, a.dim, seed=SEED)
+    graph = sd.DeepSortGraph.from_bipartite(bg, feats)
+    del bg
+    torch.cuda.empty_cache()
+    labels = torch.cat([torch.full((a.genes,), -1, dtype=torch.int64),
+                        torch.randint(0, NUM_CLASSES, (a.cells,), generator=torch.Generator().manual_seed(SEED))]).to(dev)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    torch.manual_seed(SEED)
+    model = sd.GNN(a.dim, a.hidden, NUM_CLASSES, a.layers, a.genes, activation=torch.relu, dropout=0.0).to(dev)
+    parallel.broadcast_params(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    lo, hi = parallel.cell_ranges(a.cells, world)[rank]
+    seeds = torch.arange(a.genes + lo, a.genes + hi, device=dev)
+    sampler = sd.NeighborSampler(graph, a.batch, num_hops=a.layers, neighbor_type='in', shuffle=True, seed_nodes=seeds,
+                                 fanouts=fanouts, seed=SEED + rank, generator=torch.Generator(device=dev).manual_seed(SEED + rank))
+    it = iter(sampler)
+    sizes = []
+
+    def step():
+        nf = next(it)
+        nf.copy_from_parent()
+        logits = model(nf)
+        loss = torch.nn.functional.cross_entropy(logits, labels[nf.layer_parent_nid(-1)], reduction="sum")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        parallel.allreduce_grads(model)
+        opt.step()
+        sizes.append([nf.layer_size(i) for i in range(nf.num_layers)] + [nf.block_size(i) for i in range(nf.num_blocks)])
+        return loss
+
+    for _ in range(a.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sd._lib.launch_count(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        loss = step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "cells/sec (forward+backward), neighbour-sampled mini-batches", "value": world * a.batch / (ms / 1e3),
+            "unit": "cells/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic {a.cells} cells x {a.genes} genes, avg-degree {int(a.deg)}, {a.layers}-layer "
+                                   f"hidden={a.hidden}, fan-outs {fanouts}, {a.batch} seed cells per GPU per step, graph replicated",
+                       "graph_build_s": build_s, "graph_edges": graph.number_of_edges(),
+                       "last_flow_layers_then_blocks": sizes[-1], "final_loss_per_cell": float(loss) / a.batch},
+            "gpu_launches": sd._lib.launch_count(), "roofline": None, "cpu_baseline": None, "e2e": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "sampled":
+        run_sampled(args)
     else:
         run_ours(args)

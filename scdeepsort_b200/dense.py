@@ -30,19 +30,29 @@ def split_tf32(x: torch.Tensor, mask_src: torch.Tensor = None, want_masked=False
     return hi, lo, masked
 
 
+_MAX_N = 512      # TMEM columns of one CTA: wider outputs are produced in column blocks
+
+
 def linear_tc(a_hi, a_lo, b_hi, b_lo, m, n, k, bias=None, relu=False):
     out = torch.empty(m, n, device=a_hi.device, dtype=torch.float32)
     lib = _lib.load()
-    _lib.check(lib.wsage_linear_tc(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi), _ptr(b_lo), b_hi.stride(0),
-                                   _ptr(bias), 1 if relu else 0, _ptr(out), out.stride(0), m, n, k, _stream()),
-               "wsage_linear_tc")
+    blocks = (n + _MAX_N - 1) // _MAX_N
+    step = -(-n // blocks)
+    step += -step % 16                       # equal-ish column blocks, multiples of 16
+    for n0 in range(0, n, step):
+        nc = min(step, n - n0)
+        o = out[:, n0:n0 + nc]
+        _lib.check(lib.wsage_linear_tc(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi[n0:]), _ptr(b_lo[n0:]), b_hi.stride(0),
+                                       _ptr(bias[n0:]) if bias is not None else None, 1 if relu else 0,
+                                       _ptr(o), out.stride(0), m, nc, k, _stream()), "wsage_linear_tc")
     return out
 
 
 def tc_supported(in_features: int, out_features: int) -> bool:
     """Shapes the tensor-core kernel takes in both directions (forward N = out, input-gradient N = in):
-    widths that are multiples of 4 (16-byte fp32 rows for the split kernel) and at most 512 (TMEM columns)."""
-    return in_features % 4 == 0 and out_features % 4 == 0 and 0 < in_features <= 512 and 0 < out_features <= 512
+    widths that are multiples of 4 (16-byte fp32 rows for the split kernel); outputs wider than 512 (TMEM
+    columns) are produced in column blocks."""
+    return in_features % 4 == 0 and out_features % 4 == 0 and in_features > 0 and out_features > 0
 
 
 class _LinearReluTC(torch.autograd.Function):

@@ -67,6 +67,42 @@ class DeepSortGraph:
                              self.in_weight.to(device), {k: v.to(device) for k, v in self.ndata.items()})
 
     @classmethod
+    def from_bipartite(cls, bg: "BipartiteGraph", features=None):
+        """Device-side build of the reference-contract graph (normalised weights, unit self-loop last in every
+        row) from the factored full-graph structures — the vectorised form of normalize_weight + add_edges
+        (utils/preprocess_internal.py:15-23,170-173,211-214) for atlases whose edge list never exists on the
+        host.  Every cell must be a support cell.  ``in_src`` is int32 (N < 2^31) to halve its footprint."""
+        assert bg.num_support == bg.num_cells, "test cells (gene->cell only) need the host builder"
+        dev, g, c = bg.device, bg.num_genes, bg.num_cells
+        n = g + c
+
+        def cols(csr):
+            col = csr.col.to(torch.int32)
+            return col & 0xFFFF if csr.col_bits == _lib.COL_U16 else col
+
+        deg = torch.cat([bg.gene_csr.rowptr[1:] - bg.gene_csr.rowptr[:-1], bg.cell_csr.rowptr[1:] - bg.cell_csr.rowptr[:-1]])
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        rowptr[1:] = torch.cumsum(deg + 1, 0)
+        e_total = int(rowptr[-1])
+        src = torch.empty(e_total, dtype=torch.int32, device=dev)
+        w = torch.empty(e_total, dtype=torch.float32, device=dev)
+        for csr, norm, row0, col_off in ((bg.gene_csr, bg.norm_g, 0, g), (bg.cell_csr, bg.norm_c, g, 0)):
+            d = csr.rowptr[1:] - csr.rowptr[:-1]
+            row_of = torch.repeat_interleave(torch.arange(csr.n_dst, device=dev), d, output_size=csr.nnz)
+            pos = torch.arange(csr.nnz, device=dev) + row_of + int(rowptr[row0])      # one self-loop slot per earlier row
+            src[pos] = cols(csr) + col_off
+            w[pos] = csr.x * norm[row_of]
+            del row_of, pos
+        loops = rowptr[1:] - 1
+        src[loops] = torch.arange(n, dtype=torch.int32, device=dev)
+        w[loops] = 1.0
+        node_id = torch.cat([torch.arange(g, dtype=torch.int32, device=dev), torch.full((c,), -1, dtype=torch.int32, device=dev)])
+        nd = {"id": node_id}
+        if features is not None:
+            nd["features"] = features
+        return cls(g, c, rowptr, src, w, nd)
+
+    @classmethod
     def from_edges(cls, src, dst, weight, node_id, features, num_genes):
         """From a COO edge list with final weights (e.g. arrays exported from a reference DGLGraph)."""
         src = torch.as_tensor(src, dtype=torch.int64)

@@ -155,7 +155,7 @@ class NeighborSampler:
             dst_nodes = layer_nid[hop]
             eid, deg = _in_edges(g, dst_nodes, self.fanouts[self.num_hops - hop], self.generator,
                                  seed=self.seed + 1000003 * self._batch + hop)
-            src_parent = g.in_src[eid]
+            src_parent = g.in_src[eid].to(torch.int64)
             src_nodes = torch.unique(src_parent)                   # sorted parent ids
             layer_nid[hop - 1] = src_nodes
             col = torch.searchsorted(src_nodes, src_parent).to(torch.int32)

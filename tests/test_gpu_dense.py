@@ -28,7 +28,8 @@ def test_split_tf32_reconstructs_fp32():
                                              (129, 32, 16, True, False), (5003, 200, 400, True, True),
                                              (777, 48, 256, False, False), (20000, 400, 208, True, True),
                                              (300, 400, 16, False, True), (1, 64, 64, True, True),
-                                             (1102, 400, 200, True, True), (259, 48, 40, True, True), (700, 40, 12, False, True)])
+                                             (1102, 400, 200, True, True), (259, 48, 40, True, True), (700, 40, 12, False, True),
+                                             (3000, 400, 800, True, True), (1500, 800, 800, True, True)])
 def test_linear_tc_forward_backward(m, k, n, relu, bias):
     assert dense.tc_supported(k, n)
     g = torch.Generator(device="cpu").manual_seed(m + k + n)
@@ -57,8 +58,12 @@ def test_linear_tc_forward_backward(m, k, n, relu, bias):
 def test_unsupported_shapes_are_rejected():
     assert dense.tc_supported(400, 40) and dense.tc_supported(400, 200)    # N is padded to 16 inside the kernel
     assert not dense.tc_supported(18, 64)        # K not a multiple of 4
-    assert not dense.tc_supported(400, 516)      # more than 512 TMEM columns
+    assert dense.tc_supported(400, 800)          # > 512 TMEM columns: done in column blocks by the wrapper
+    import ctypes
+    lib = sd._lib.load()
     a = torch.zeros(8, 48, device=DEV)
     b = torch.zeros(520, 48, device=DEV)
-    with pytest.raises(RuntimeError, match="512"):
-        dense.linear_tc(a, a, b, b, 8, 520, 48)
+    o = torch.zeros(8, 520, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
+    rc = lib.wsage_linear_tc(p(a), p(a), 48, p(b), p(b), 48, None, 0, p(o), 520, 8, 520, 48, None)
+    assert rc == sd._lib.EINVAL and b"512" in lib.wsage_last_error()    # the raw ABI call takes N <= 512
