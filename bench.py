@@ -327,7 +327,7 @@ def run_sampled(a):
     torch.manual_seed(SEED)
     model = sd.GNN(a.dim, a.hidden, NUM_CLASSES, a.layers, a.genes, activation=torch.relu, dropout=0.0).to(dev)
     parallel.broadcast_params(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    opt = sd.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
     lo, hi = parallel.cell_ranges(a.cells, world)[rank]
     seeds = torch.arange(a.genes + lo, a.genes + hi, device=dev)
     sampler = sd.NeighborSampler(graph, a.batch, num_hops=a.layers, neighbor_type='in', shuffle=True, seed_nodes=seeds,
@@ -339,7 +339,7 @@ def run_sampled(a):
         nf = next(it)
         nf.copy_from_parent()
         logits = model(nf)
-        loss = torch.nn.functional.cross_entropy(logits, labels[nf.layer_parent_nid(-1)], reduction="sum")
+        loss = sd.optim.cross_entropy_sum(logits, labels[nf.layer_parent_nid(-1)])
         opt.zero_grad(set_to_none=True)
         loss.backward()
         parallel.allreduce_grads(model)

@@ -162,6 +162,22 @@ int wsage_sample_neighbors(const int64_t* rowptr, const int64_t* nodes, int64_t 
                            int32_t fanout, uint64_t seed, int64_t* out_eid, int32_t* out_deg,
                            void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Loss and optimiser step of the training inner loop.
+ *
+ * wsage_softmax_ce: CrossEntropyLoss(reduction='sum') of /root/reference/train.py:36,82.  One launch
+ *   computes per-block loss partials (loss_partial[0..n_partial), summed by the caller in index order:
+ *   deterministic) and, if d_logits != NULL, the gradient softmax(logits) - onehot(labels).
+ *   labels are int64 class indices in [0, k).
+ * wsage_adam_step: one torch.optim.Adam(lr, betas, eps, weight_decay) update of n parameters
+ *   (train.py:34-35,85; L2 decay added to the gradient, bias correction with `step` >= 1).
+ * ------------------------------------------------------------------------------------- */
+int wsage_softmax_ce(const float* logits, int64_t ld, const int64_t* labels, int64_t m, int32_t k,
+                     float* d_logits, int64_t ld_d, float* loss_partial, int32_t n_partial, void* stream);
+int wsage_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                    void* stream);   /* hyper-parameters in double: 1-beta and lr/(1-beta1^step) are formed in fp64 as torch does */
+
 #ifdef __cplusplus
 }
 #endif

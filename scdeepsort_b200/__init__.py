@@ -3,7 +3,7 @@
 Host side in Python/PyTorch (mirroring /root/reference/models/gnn.py and the DGL NodeFlow
 surface), arithmetic in hand-written sm_100a CUDA behind the C ABI of ``include/wsage.h``.
 """
-from . import _lib, dense, parallel
+from . import _lib, dense, optim, parallel
 from .gnn import GNN, NodeUpdate, predict_labels
 from .graph import BipartiteGraph, DeepSortGraph
 from .nodeflow import FullGraphFlow, NeighborSampler, NodeFlow

@@ -18,7 +18,8 @@ ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
            "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm",
-           "wsage_split_tf32", "wsage_linear_tc", "wsage_sample_neighbors")
+           "wsage_split_tf32", "wsage_linear_tc", "wsage_sample_neighbors",
+           "wsage_softmax_ce", "wsage_adam_step")
 
 
 class SpmmArgs(Structure):
@@ -81,6 +82,11 @@ def load():
                                     c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p]
     lib.wsage_sample_neighbors.restype = c_int32
     lib.wsage_sample_neighbors.argtypes = [c_void_p, c_void_p, c_int64, c_int32, ctypes.c_uint64, c_void_p, c_void_p, c_void_p]
+    lib.wsage_softmax_ce.restype = c_int32
+    lib.wsage_softmax_ce.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p]
+    lib.wsage_adam_step.restype = c_int32
+    lib.wsage_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int32, c_void_p]
     _lib = lib
     return lib
 

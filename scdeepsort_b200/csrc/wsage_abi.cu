@@ -3,6 +3,8 @@
 #include "agg_tiled.cuh"
 #include "dense_tc.cuh"
 #include "sampler.cuh"
+#include "loss_adam.cuh"
+#include <math.h>
 
 using namespace wsage;
 
@@ -184,6 +186,30 @@ int wsage_sample_neighbors(const int64_t* rowptr, const int64_t* nodes, int64_t 
     sample_neighbors_kernel<<<gather_grid(n_nodes), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         rowptr, nodes, n_nodes, fanout, seed, out_eid, out_deg);
     return check_launch("sample_neighbors");
+}
+
+int wsage_softmax_ce(const float* logits, int64_t ld, const int64_t* labels, int64_t m, int32_t k,
+                     float* d_logits, int64_t ld_d, float* loss_partial, int32_t n_partial, void* stream) {
+    WSAGE_REQUIRE(m >= 0 && k > 0 && n_partial >= 1, "bad shape");
+    WSAGE_REQUIRE(loss_partial, "null loss_partial");
+    WSAGE_REQUIRE(m == 0 || (logits && labels && ld >= k && (!d_logits || ld_d >= k)), "null pointer or bad leading dimension");
+    softmax_ce_kernel<<<n_partial, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, labels, m, k, d_logits, ld_d, loss_partial);
+    return check_launch("softmax_ce");
+}
+
+int wsage_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                    void* stream) {
+    WSAGE_REQUIRE(n >= 0 && step >= 1, "n < 0 or step < 1");
+    if (n == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(param && grad && exp_avg && exp_avg_sq, "null pointer");
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
+    adam_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), (float)beta1, (float)(1.0 - beta1),
+                                                                      (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)sqrt(bc2));
+    return check_launch("adam_step");
 }
 
 }  // extern "C"

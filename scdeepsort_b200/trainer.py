@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from .gnn import GNN, predict_labels
 from .graph import BipartiteGraph, DeepSortGraph
 from .nodeflow import FullGraphFlow, NeighborSampler
+from .optim import Adam, cross_entropy_sum
 
 
 class Trainer:
@@ -35,8 +36,8 @@ class Trainer:
         self.num_labels, self.n_layers, self.batch_size, self.unsure_rate = num_labels, n_layers, batch_size, unsure_rate
         self.model = GNN(in_feats=dense_dim, n_hidden=hidden_dim, n_classes=num_labels, n_layers=n_layers,
                          gene_num=graph.num_genes, activation=F.relu, dropout=dropout).to(self.device)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)
-        self.loss_fn = nn.CrossEntropyLoss(reduction='sum')
+        self.optimizer = Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)     # train.py:34-35
+        self.loss_fn = cross_entropy_sum                                                     # train.py:36
         n = graph.number_of_nodes()
         self.num_neighbors = n if num_neighbors == 0 else num_neighbors        # train.py:37-40
         self.save_path = Path(save_path) if save_path else None
@@ -148,7 +149,7 @@ class FullGraphTrainer:
         self.model = GNN(in_feats=dense_dim, n_hidden=hidden_dim, n_classes=num_labels, n_layers=n_layers,
                          gene_num=graph.num_genes, activation=F.relu, dropout=dropout).to(self.device)
         self.model.spmm_algo = spmm_algo
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)
+        self.optimizer = Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)
         self.sharded = sharded
         self._dev_feat = self._dev_lab = None
 
@@ -170,7 +171,7 @@ class FullGraphTrainer:
             logits = sharded_forward(self.model, self.graph, feats)
         else:
             logits = self.model(FullGraphFlow(self.graph, feats))
-        return F.cross_entropy(logits, lab, reduction='sum'), logits
+        return cross_entropy_sum(logits, lab), logits
 
     def step(self, features, labels, return_loss=True):
         loss, _ = self.forward_loss(features, labels)
