@@ -177,3 +177,22 @@ def test_sampler_batches_shuffle_and_fanout(golden_train):
     assert len(seen) == len(sampler) == (len(seeds) + 49) // 50
     allseen = torch.cat(seen)
     assert torch.equal(torch.sort(allseen).values, torch.sort(seeds).values) and not torch.equal(allseen, seeds)
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without libwsage.so the binding raises instead of computing something else."""
+    monkeypatch.setattr(sd._lib, "_lib", None)
+    monkeypatch.setattr(sd._lib, "LIB_PATH", tmp_path / "libwsage.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sd._lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under scdeepsort_b200/ (nor bench.py's GPU arm) may route through it."""
+    for path in (ROOT / "scdeepsort_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, path
+    bench = (ROOT / "bench.py").read_text()
+    gpu_arm = bench[bench.index("def run_ours"):bench.index("def run_sampled")]
+    # the only oracle use inside run_ours is the bounded cpu_baseline leg (cpu_reference_steps)
+    assert "from oracle" not in gpu_arm and gpu_arm.count("cpu_reference_steps(") == 1
