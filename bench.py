@@ -253,7 +253,18 @@ def run_ours(a):
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "ms_per_launch": g["ms"] / g["n"],
                     "gather_side_tbs": g["gather_bytes"] / g["ms"] / 1e9,
                     "note": "algorithmic bytes count distinct rows once (SURVEY 8d); the E*D gather is served "
-                            "on-chip (L2/L1/smem), reported as gather_side_tbs"}
+                            "on-chip (L2/L1/smem), reported as gather_side_tbs and bounded by onchip"}
+        if key[0] == "tiled":
+            # the resource that actually binds this kernel: the LSU / shared-memory data pipe, 1 wavefront (128 B)
+            # per clock per SM; per edge the kernel issues ceil(row bytes / 128) LDS wavefronts for the source
+            # row + 1 broadcast LDS.64 for the edge's (column, value)
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            wf_per_edge = -(-a.dim * 4 // 128) + 1
+            nnz = sum(t["nnz"] for t in timing if (t["algo"] == 2) and (("gene<-cell" if t["n_dst"] == a.genes else "cell<-gene") == key[1]))
+            achieved_wf = nnz * wf_per_edge / (g["ms"] / 1e3)
+            peak_wf = 148 * sm_mhz * 1e6
+            roofline["onchip"] = {"bound": "lsu_shared_pipe", "unit": "wavefronts/s", "achieved": achieved_wf, "peak": peak_wf,
+                                  "frac": achieved_wf / peak_wf, "wavefronts_per_edge": wf_per_edge, "sm_mhz": sm_mhz}
 
     # ---- end-to-end through the public API with HOST buffers: `e2e` --------------------------
     e2e = None
