@@ -180,13 +180,16 @@ def test_synthetic_golden_both_paths(golden_syn, tag, n_layers):
     assert rel_err(b, z[f"{tag}/L{n_layers}/logits"]) < 1e-5
 
 
-@pytest.mark.parametrize("n_src,dim,algo", [(300, 64, 1), (70000, 32, 1), (300, 18, 1), (300, 400, 0), (300, 400, 2), (5000, 128, 2)])
+@pytest.mark.parametrize("n_src,dim,algo", [(300, 64, 1), (70000, 32, 1), (300, 18, 1), (300, 400, 0), (300, 400, 2), (5000, 128, 2),
+                                            (2000, 200, 2), (700, 132, 2), (900, 512, 2), (70000, 400, 2), (43, 400, 2), (1, 64, 2)])
 def test_spmm_all_outputs(n_src, dim, algo):
     """wsage_spmm epilogue options (dscale / self / raw / dot / row_perm, uint16 and int32 columns)."""
     rng = np.random.default_rng(n_src + dim)
     n_dst = 211
     deg = rng.integers(0, 60, n_dst); deg[:3] = [0, 1, 59]
     rowptr = np.zeros(n_dst + 1, dtype=np.int64); rowptr[1:] = np.cumsum(deg)
+    deg = np.minimum(deg, n_src)
+    rowptr[1:] = np.cumsum(deg)
     col = np.concatenate([np.sort(rng.choice(n_src, d, replace=False)) for d in deg]).astype(np.int64)
     x = rng.uniform(0.05, 9, rowptr[-1]).astype(np.float32)
     hs = torch.from_numpy(rng.normal(0, 1, (n_src, dim)).astype(np.float32))
@@ -210,6 +213,9 @@ def test_spmm_all_outputs(n_src, dim, algo):
     assert rel_err(dot.cpu(), (acc * q.double()).sum(1)) < 1e-5
     out2, _, _ = sd.spmm(csr, hs.to(DEV), algo=algo)      # plain Σ, no epilogue terms
     assert rel_err(out2.cpu(), acc) < 1e-5
+    csr.row_perm = None                                   # identity row order
+    out3, _, _ = sd.spmm(csr, hs.to(DEV), algo=algo)
+    assert rel_err(out3.cpu(), acc) < 1e-5
 
 
 def test_wrapper_rejects_bad_inputs():
