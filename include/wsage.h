@@ -120,7 +120,22 @@ typedef struct wsage_spmm_args {
     int32_t        algo;
     void*          workspace;
     size_t         workspace_bytes;
+    /* Optional dense block (ABI >= 1001): entries of the popular genes, removed from the CSR and stored
+     * zero-filled as xd[tile][k][T] (T = wsage_dense_tile(), tile = destination slot / T, k = source
+     * index), handled by an FMA-bound kernel whose sums seed the CSR kernel's accumulators:
+     *   acc[v,:] += SUM_k xd[slot(v)/T][k][slot(v)%T] * hs[src(k),:]
+     * src(k) = dense_src_ids[k] (NULL: k, then dense_k == n_src).  slot(v) = dense_dst_map[v]
+     * (< 0: row not in the block.  NULL: v, then dense_t == n_dst).  Needs the tiled kernel's
+     * preconditions (dim % 4 == 0, dim <= 512, contiguous 16-byte aligned hs). */
+    const float*   dense_x;        /* NULL = no dense block                                  */
+    int64_t        dense_k;        /* sources of the block                                   */
+    int64_t        dense_t;        /* destination slots of the block                         */
+    const int32_t* dense_src_ids;  /* [dense_k] or NULL                                      */
+    const int32_t* dense_dst_map;  /* [n_dst]  or NULL                                       */
 } wsage_spmm_args;
+
+/* Destination slots per tile of the dense block's blocked layout. */
+int wsage_dense_tile(void);
 
 size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a);
 /* The kernel wsage_spmm would run for these arguments: 1 (gather) or 2 (tiled); 0 on bad args. */

@@ -17,7 +17,7 @@ COL_I32, COL_U16 = 32, 16
 ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
-           "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm",
+           "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_dense_tile",
            "wsage_split_tf32", "wsage_linear_tc", "wsage_sample_neighbors",
            "wsage_softmax_ce", "wsage_adam_step")
 
@@ -31,6 +31,8 @@ class SpmmArgs(Structure):
         ("out", c_void_p), ("ld_out", c_int64), ("raw", c_void_p), ("ld_raw", c_int64),
         ("q", c_void_p), ("ld_q", c_int64), ("dot", c_void_p), ("row_perm", c_void_p),
         ("algo", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("dense_x", c_void_p), ("dense_k", c_int64), ("dense_t", c_int64),
+        ("dense_src_ids", c_void_p), ("dense_dst_map", c_void_p),
     ]
 
 
@@ -74,6 +76,7 @@ def load():
     lib.wsage_spmm_algo.argtypes = [POINTER(SpmmArgs)]
     lib.wsage_spmm.restype = c_int32
     lib.wsage_spmm.argtypes = [POINTER(SpmmArgs), c_void_p]
+    lib.wsage_dense_tile.restype = c_int32
     lib.wsage_split_tf32.restype = c_int32
     lib.wsage_split_tf32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                      c_void_p, c_int64, c_int64, c_int32, c_void_p]

@@ -55,6 +55,13 @@ struct TiledParams {
     int n_splits;
     int win_per_split;
     const int32_t* row_perm;
+    int l2_prefetch;          // > 0: some CTAs prefetch the window this many windows ahead into L2
+    // accumulators start from the dense block's sums (agg_dense.cuh): init[slab][slot][dim], slabs added in
+    // index order by the split-0 CTA of the row; slot = init_map[row] (< 0: none) or the row itself
+    const float* init;
+    int init_slabs;
+    int64_t init_rows;
+    const int32_t* init_map;
     // epilogue (n_splits == 1) ...
     const float* dscale;
     const float* selfcoef;
@@ -90,6 +97,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bulk prefetch of a contiguous global range into L2 (no completion tracking).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -207,6 +218,13 @@ agg_tiled_kernel(const TiledParams p) {
             const int64_t row0 = (int64_t)w * p.win_rows;
             const int rows = (int)min((int64_t)p.win_rows, p.n_src - row0);
             const uint32_t row_bytes = (uint32_t)(dim * sizeof(float));
+            if (p.l2_prefetch > 0 && (tile & 7) == 0 && lane == 0 && w + p.l2_prefetch < w_end) {
+                // tables larger than L2 (cell rows): one CTA in eight pulls a window further ahead into L2,
+                // so the ring's own copies (all resident CTAs stream the same slice) find it there
+                const int64_t prow0 = (int64_t)(w + p.l2_prefetch) * p.win_rows;
+                const int prows = (int)min((int64_t)p.win_rows, p.n_src - prow0);
+                bulk_prefetch_l2(p.hs + prow0 * dim, prows * row_bytes);
+            }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes);
             __syncwarp();
             for (int r = lane; r < rows; r += 32)
@@ -225,7 +243,10 @@ agg_tiled_kernel(const TiledParams p) {
     float cx[R], nx[R];     // this lane's value   in the current / prefetched chunk
     RowAcc<DIM> acc[R];
 
-    // lane-private fetch of edge (chunk_base + lane); sentinel past the row end
+    // lane-private fetch of edge (chunk_base + lane); sentinel past the row end.  (ncu attributes 11 % of the
+    // stall samples to the select that follows these loads; a clamped-index variant without the select removed
+    // the stall but not a microsecond of run time — the kernel is throughput-bound on the shared-memory pipe —
+    // and its extra ballot predicate cost 5 %, so the sentinel form stays.)
     auto fetch = [&](int r, int chunk_base, int& c_out, float& x_out) {
         const int e = chunk_base + lane;
         if (e < len[r]) {
@@ -247,6 +268,21 @@ agg_tiled_kernel(const TiledParams p) {
             len[r] = (int)(p.rowptr[row[r] + 1] - beg[r]);
         }
         acc[r].zero();
+        if (p.init != nullptr && split == 0 && row[r] >= 0) {
+            const int64_t slot = p.init_map ? (int64_t)__ldg(p.init_map + row[r]) : row[r];
+            if (slot >= 0) {
+                for (int k = 0; k < p.init_slabs; ++k) {
+                    const float* src = p.init + ((size_t)k * p.init_rows + slot) * dim;
+#pragma unroll
+                    for (int j = 0; j < S::N4; ++j) {
+                        if (!S::on4(j, lane, dim)) continue;
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(src + (j * 32 + lane) * 4));
+                        acc[r].v4[j].x += t.x; acc[r].v4[j].y += t.y; acc[r].v4[j].z += t.z; acc[r].v4[j].w += t.w;
+                    }
+                    if (S::TAIL1 && S::on1(lane)) acc[r].v1 += __ldg(src + S::J4 * 128 + lane);
+                }
+            }
+        }
     }
     if (w_begin > 0) {
         // first edge with col >= first column of this split: lane r searches row r, then broadcast
@@ -408,7 +444,7 @@ tiled_reduce_kernel(const TiledParams p) {
 // WSAGE_TILED_VARIANT (env, tuning only) selects among the compiled shapes for dim == 400.
 struct TiledVariant { int nw, r, stages; bool esm; };
 // [0] = default (best of the round-1 sweeps, profiles/r01_summary.md)
-constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}};
+constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}, {12, 4, 2, true}};
 constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
 
 inline int tiled_variant_index() {
@@ -487,13 +523,22 @@ inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
     return reuse >= 1.5 && a->nnz >= (int64_t)1 << 20;
 }
 
+struct TiledInit { const float* init; int slabs; int64_t rows; const int32_t* map; };
+
 template <typename ColT, int DIM, int NW, int R, int STG, bool ESM>
-int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
+int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const TiledInit& ini, cudaStream_t st) {
     TiledParams p{};
+    p.init = ini.init; p.init_slabs = ini.slabs; p.init_rows = ini.rows; p.init_map = ini.map;
     p.rowptr = a->rowptr; p.col = a->col; p.x = a->x; p.hs = a->hs;
     p.n_src = a->n_src; p.n_dst = a->n_dst; p.dim = a->dim;
     p.win_rows = pl.win_rows; p.pitch = pl.pitch; p.n_windows = pl.n_windows; p.n_tiles = pl.n_tiles;
     p.n_splits = pl.n_splits; p.win_per_split = pl.win_per_split; p.row_perm = a->row_perm;
+    {   // WSAGE_TILED_L2PF (env, tuning only): prefetch distance in windows
+        static const int forced = [] { const char* e = getenv("WSAGE_TILED_L2PF"); return e ? atoi(e) : -1; }();
+        const bool big = (double)a->n_src * a->dim * sizeof(float) > 64.0 * (1 << 20);
+        p.l2_prefetch = forced >= 0 ? forced : 0;      // measured: no gain at c3/c4 (the slice is L2-resident), off
+        (void)big;
+    }
     p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
@@ -509,26 +554,27 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream
 }
 
 template <typename ColT>
-int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, cudaStream_t st) {
+int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledInit& ini, cudaStream_t st) {
     switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and the bench (400/400)
         case 400:
             switch (tiled_variant_index()) {
-                case 1: return launch_tiled_shape<ColT, 400, 12, 4, 3, false>(a, pl, st);
-                case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4, true>(a, pl, st);
-                case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, st);
-                default: return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, st);
+                case 1: return launch_tiled_shape<ColT, 400, 12, 4, 3, false>(a, pl, ini, st);
+                case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4, true>(a, pl, ini, st);
+                case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, ini, st);
+                case 4: return launch_tiled_shape<ColT, 400, 12, 4, 2, true>(a, pl, ini, st);
+                default: return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, ini, st);
             }
-        case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3, true>(a, pl, st);
-        case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3, true>(a, pl, st);
-        default:  return launch_tiled_shape<ColT, 0, 12, 4, 3, true>(a, pl, st);
+        case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3, true>(a, pl, ini, st);
+        case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3, true>(a, pl, ini, st);
+        default:  return launch_tiled_shape<ColT, 0, 12, 4, 3, true>(a, pl, ini, st);
     }
 }
 
-inline int launch_tiled(const wsage_spmm_args* a, cudaStream_t st) {
+// The split partials occupy the first tiled_plan(a).workspace_bytes of the workspace (the dense block's
+// sums, if any, follow; wsage_spmm checks the size).
+inline int launch_tiled(const wsage_spmm_args* a, const TiledInit& ini, cudaStream_t st) {
     const TiledPlan pl = tiled_plan(a);
-    if (pl.workspace_bytes > a->workspace_bytes || (pl.workspace_bytes && !a->workspace))
-        return fail(WSAGE_EINVAL, "%s: %s", "wsage_spmm", "workspace too small (see wsage_spmm_workspace_bytes)");
-    return a->col_bits == WSAGE_COL_U16 ? launch_tiled_col<uint16_t>(a, pl, st) : launch_tiled_col<int32_t>(a, pl, st);
+    return a->col_bits == WSAGE_COL_U16 ? launch_tiled_col<uint16_t>(a, pl, ini, st) : launch_tiled_col<int32_t>(a, pl, ini, st);
 }
 
 }  // namespace wsage

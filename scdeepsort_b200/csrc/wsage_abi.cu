@@ -1,6 +1,7 @@
 // extern "C" entry points of libwsage.so (declared in include/wsage.h).
 #include "agg_gather.cuh"
 #include "agg_tiled.cuh"
+#include "agg_dense.cuh"
 #include "dense_tc.cuh"
 #include "sampler.cuh"
 #include "loss_adam.cuh"
@@ -10,7 +11,9 @@ using namespace wsage;
 
 extern "C" {
 
-int wsage_version(void) { return 1000; }
+int wsage_version(void) { return 1001; }
+
+int wsage_dense_tile(void) { return kDenseT; }
 
 const char* wsage_last_error(void) { return g_err; }
 
@@ -76,6 +79,13 @@ static int spmm_validate(const wsage_spmm_args* a) {
     WSAGE_REQUIRE(!a->dot || (a->q && a->ld_q >= a->dim), "dot needs q");
     WSAGE_REQUIRE(!a->out || a->ld_out >= a->dim, "ld_out < dim");
     WSAGE_REQUIRE(!a->raw || a->ld_raw >= a->dim, "ld_raw < dim");
+    if (a->dense_x) {
+        WSAGE_REQUIRE(a->dense_k > 0 && a->dense_t > 0, "dense block needs dense_k, dense_t > 0");
+        WSAGE_REQUIRE(a->dense_src_ids || a->dense_k == a->n_src, "dense_src_ids == NULL needs dense_k == n_src");
+        WSAGE_REQUIRE(a->dense_dst_map || a->dense_t == a->n_dst, "dense_dst_map == NULL needs dense_t == n_dst");
+        WSAGE_REQUIRE(aligned16(a->dense_x), "dense_x must be 16-byte aligned");
+        WSAGE_REQUIRE(a->algo != 1, "a dense block needs the tiled kernel (algo 0 or 2)");
+    }
     return WSAGE_OK;
 }
 
@@ -87,14 +97,25 @@ static bool spmm_vec4(const wsage_spmm_args* a) {
            (!a->q || (a->ld_q % 4 == 0 && aligned16(a->q)));
 }
 
+// workspace = [tiled split partials, rounded up to 256 B][dense block sums]
+static size_t spmm_tiled_ws(const wsage_spmm_args* a, bool vec4) {
+    const bool tiled = dense_requested(a) ? tiled_supported(a, vec4) : (a->algo == 2 || (a->algo == 0 && tiled_profitable(a, vec4)));
+    if (!tiled || !tiled_supported(a, vec4)) return 0;
+    return (tiled_plan(a).workspace_bytes + 255) & ~(size_t)255;
+}
+
 size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a) {
     if (!a || spmm_validate(a) != WSAGE_OK || a->n_dst == 0) return 0;
-    return tiled_workspace_bytes(a, spmm_vec4(a));
+    const bool vec4 = spmm_vec4(a);
+    size_t n = spmm_tiled_ws(a, vec4);
+    if (dense_requested(a) && tiled_supported(a, vec4)) n += dense_plan(a).out_bytes;
+    return n;
 }
 
 int wsage_spmm_algo(const wsage_spmm_args* a) {
     if (!a || spmm_validate(a) != WSAGE_OK) return 0;
     if (a->algo != 0) return a->algo;
+    if (dense_requested(a)) return 2;
     return tiled_profitable(a, spmm_vec4(a)) ? 2 : 1;
 }
 
@@ -105,11 +126,23 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = spmm_vec4(a);
     int algo = a->algo;
-    if (algo == 0) algo = tiled_profitable(a, vec4) ? 2 : 1;
+    if (algo == 0) algo = (dense_requested(a) || tiled_profitable(a, vec4)) ? 2 : 1;
     if (algo == 2) {
         if (!tiled_supported(a, vec4))
             return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "tiled kernel needs dim % 4 == 0, contiguous 16-byte aligned hs and dim <= 512");
-        return launch_tiled(a, st);
+        const size_t tiled_ws = spmm_tiled_ws(a, vec4);
+        const size_t need = tiled_ws + (dense_requested(a) ? dense_plan(a).out_bytes : 0);
+        if (need > a->workspace_bytes || (need && !a->workspace))
+            return fail(WSAGE_EINVAL, "%s: %s", "wsage_spmm", "workspace too small (see wsage_spmm_workspace_bytes)");
+        TiledInit ini{nullptr, 0, 0, nullptr};
+        if (dense_requested(a)) {
+            const DensePlan dp = dense_plan(a);
+            float* dout = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + tiled_ws);
+            const int rc2 = launch_dense(a, dp, dout, st);
+            if (rc2 != WSAGE_OK) return rc2;
+            ini = TiledInit{dout, dp.n_splits, a->dense_t, a->dense_dst_map};
+        }
+        return launch_tiled(a, ini, st);
     }
     GatherParams p{};
     p.rowptr = a->rowptr; p.col = a->col; p.w = a->x;

@@ -24,7 +24,7 @@ import scipy.sparse as sp
 import torch
 
 from . import _lib
-from .ops import Csr
+from .ops import Csr, DenseBlock
 
 
 def _segment_sum_f32(data: np.ndarray, ptr: np.ndarray) -> np.ndarray:
@@ -177,6 +177,67 @@ def _to_csr(rowptr, col, x, n_src, n_dst, device):
                n_src, n_dst, bits, _balanced_row_perm(deg).to(device))
 
 
+def _split_dense(csr: Csr, slot: torch.Tensor, side: str, tile: int, chunk_edges: int = 1 << 27) -> Csr:
+    """Moves the entries of the popular genes (``slot[gene] >= 0``) out of ``csr`` into a ``DenseBlock``.
+
+    side == 'src': the genes are the COLUMNS of csr (cell-destination CSR); the block's sources are the
+    popular genes, its destinations every row.  side == 'dst': the genes are the ROWS (gene-destination
+    CSR); the block's sources are every column (cell), its destinations the popular genes' slots.
+    Works in row chunks so the index temporaries stay bounded at atlas scale."""
+    dev = csr.x.device
+    md = int((slot >= 0).sum())
+    n_dst, n_src = csr.n_dst, csr.n_src
+    if side == 'src':
+        k, t = md, n_dst
+        ids = torch.nonzero(slot >= 0).flatten()
+        order = torch.argsort(slot[ids])
+        src_ids, dst_map = ids[order].to(torch.int32), None
+    else:
+        k, t = n_src, md
+        src_ids, dst_map = None, slot.to(torch.int32)
+    n_tiles = (t + tile - 1) // tile
+    xd = torch.zeros(n_tiles * k * tile, dtype=torch.float32, device=dev)
+    rowptr_h = csr.rowptr.cpu()
+    deg = csr.rowptr[1:] - csr.rowptr[:-1]
+    new_deg = torch.zeros(n_dst, dtype=torch.int64, device=dev)
+    cols, vals = [], []
+    moved = 0
+    r0 = 0
+    while r0 < n_dst:
+        # largest r1 with rowptr[r1] - rowptr[r0] <= chunk_edges (at least one row)
+        r1 = int(torch.searchsorted(rowptr_h, rowptr_h[r0] + chunk_edges, right=True)) - 1
+        r1 = min(max(r1, r0 + 1), n_dst)
+        e0, e1 = int(rowptr_h[r0]), int(rowptr_h[r1])
+        if e1 > e0:
+            col = csr.col[e0:e1].to(torch.int64)
+            if csr.col_bits == _lib.COL_U16:
+                col = col & 0xFFFF
+            row = torch.repeat_interleave(torch.arange(r0, r1, device=dev), deg[r0:r1], output_size=e1 - e0)
+            x = csr.x[e0:e1]
+            if side == 'src':
+                s_e = slot[col]
+                hit = s_e >= 0
+                idx = ((row[hit] // tile) * k + s_e[hit]) * tile + row[hit] % tile
+            else:
+                s_e = slot[row]
+                hit = s_e >= 0
+                idx = ((s_e[hit] // tile) * k + col[hit]) * tile + s_e[hit] % tile
+            xd[idx] = x[hit]
+            moved += int(hit.sum())
+            keep = ~hit
+            cols.append(csr.col[e0:e1][keep])
+            vals.append(x[keep])
+            new_deg[r0:r1] = torch.zeros(r1 - r0, dtype=torch.int64, device=dev).index_add_(0, row - r0, keep.to(torch.int64))
+            del col, row, s_e, hit, idx, keep
+        r0 = r1
+    rp = torch.zeros(n_dst + 1, dtype=torch.int64, device=dev)
+    rp[1:] = torch.cumsum(new_deg, 0)
+    col_new = torch.cat(cols) if cols else csr.col[:0]
+    x_new = torch.cat(vals) if vals else csr.x[:0]
+    return Csr(rp, col_new, x_new, n_src, n_dst, csr.col_bits, _balanced_row_perm(new_deg),
+               DenseBlock(xd, k, t, src_ids, dst_map, moved))
+
+
 @dataclass
 class BipartiteGraph:
     """Full-graph factorisation.  ``cell_csr`` rows = all cells (support then test), columns =
@@ -201,7 +262,7 @@ class BipartiteGraph:
 
     @property
     def nnz(self):
-        return self.cell_csr.nnz
+        return self.cell_csr.nnz + (self.cell_csr.dense.nnz if self.cell_csr.dense is not None else 0)
 
     @classmethod
     def from_expression(cls, x_support, x_test=None, threshold=0.0, device="cpu"):
@@ -225,6 +286,48 @@ class BipartiteGraph:
             xt = xa.tocsc(); xt.sort_indices()
             out.cell_csr_t = _to_csr(xt.indptr, xt.indices, xt.data, xa.shape[0], g, device)
         return out
+
+    def densify(self, threshold: float = 0.3, max_bytes: int = 32 << 30, directions=("gene",)) -> "BipartiteGraph":
+        """Splits X = X_sparse + X_dense IN PLACE for the full-graph path: genes expressed in at least
+        ``threshold`` of the (local) support cells leave the CSRs and become zero-filled dense blocks
+        (``Csr.dense``), which wsage_spmm runs on the FMA-bound dense-block kernel before the CSR walk.
+        Results are unchanged up to fp32 summation order.  The popular set is capped so that the blocks
+        stay within ``max_bytes``.  ``directions``: "gene" splits the gene-destination CSR(s) (whole dense
+        destination tiles leave the CSR walk, whose remaining tiles are unaffected: the profitable case),
+        "cell" also splits the cell-destination CSR (every row gets thinner, which costs the CSR walk
+        efficiency: measured no gain at 10 % density, kept for denser atlases).  Not for the mini-batch
+        surface (``DeepSortGraph.from_bipartite`` needs the complete CSRs)."""
+        if getattr(self, "densified", False) or self.gene_csr.n_src == 0 or self.nnz == 0:
+            return self
+        dev = self.device
+        gcsr = self.gene_csr
+        deg_g = (gcsr.rowptr[1:] - gcsr.rowptr[:-1])
+        rho = deg_g.to(torch.float64) / float(gcsr.n_src)
+        cand = torch.nonzero(rho >= threshold).flatten()
+        do_gene, do_cell = "gene" in directions, "cell" in directions
+        n_blocks = (int(do_gene) * (2 if self.cell_csr_t is not None else 1)) + int(do_cell)
+        if n_blocks == 0:
+            return self
+        cap = int(max_bytes // (4 * n_blocks * max(1, self.num_cells)))
+        if cand.numel() > cap:                       # keep the most popular ones
+            cand = cand[torch.argsort(deg_g[cand], descending=True)[:cap]]
+            cand = torch.sort(cand).values
+        if cand.numel() == 0:
+            return self
+        slot = torch.full((self.num_genes,), -1, dtype=torch.int64, device=dev)
+        slot[cand] = torch.arange(cand.numel(), device=dev)
+        tile = int(_lib.load().wsage_dense_tile())
+        new_cell = _split_dense(self.cell_csr, slot, 'src', tile) if do_cell else self.cell_csr
+        new_gene = _split_dense(self.gene_csr, slot, 'dst', tile) if do_gene else self.gene_csr
+        new_t = self.cell_csr_t
+        if do_gene and new_t is not None:
+            new_t = _split_dense(new_t, slot, 'dst', tile)
+        if new_cell.nnz == 0 or new_gene.nnz == 0 or (new_t is not None and new_t.nnz == 0):
+            return self                              # the CSR walk needs a non-empty remainder
+        self.cell_csr, self.gene_csr, self.cell_csr_t = new_cell, new_gene, new_t
+        self.densified = True
+        self.dense_genes = cand
+        return self
 
     def transpose_of_cell_csr(self) -> Csr:
         if self.cell_csr_t is not None:

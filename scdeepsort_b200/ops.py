@@ -103,6 +103,18 @@ def block_aggregate(h, alpha, block: Block, src_id, dst_id, gene_num: int):
 
 
 @dataclass
+class DenseBlock:
+    """Entries of the popular genes, taken out of a ``Csr`` and stored zero-filled and tile-blocked
+    (``x[tile][k][T]``, T = ``wsage_dense_tile()``; see include/wsage.h and csrc/agg_dense.cuh)."""
+    x: torch.Tensor                              # fp32 [n_tiles * k * T]
+    k: int                                       # sources of the block
+    t: int                                       # destination slots of the block
+    src_ids: Optional[torch.Tensor] = None       # int32 [k] rows of hs (None: source k = row k)
+    dst_map: Optional[torch.Tensor] = None       # int32 [n_dst] destination row -> slot, -1 = not in the block
+    nnz: int = 0                                 # expression entries the block stands for
+
+
+@dataclass
 class Csr:
     """Destination-major CSR of RAW expression values for the full-graph path."""
     rowptr: torch.Tensor            # int64 [n_dst+1]
@@ -112,6 +124,7 @@ class Csr:
     n_dst: int
     col_bits: int = _lib.COL_I32
     row_perm: Optional[torch.Tensor] = None   # int32 [n_dst] warp-assignment order (load balance)
+    dense: Optional[DenseBlock] = None        # entries removed from col/x and handled by the dense-block kernel
 
     @property
     def nnz(self):
@@ -153,6 +166,10 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
     if csr.row_perm is not None:
         a.row_perm = _ptr(csr.row_perm)
     a.algo = algo
+    if csr.dense is not None:
+        d = csr.dense
+        a.dense_x, a.dense_k, a.dense_t = _ptr(d.x), d.k, d.t
+        a.dense_src_ids, a.dense_dst_map = _ptr(d.src_ids), _ptr(d.dst_map)
     lib = _lib.load()
     nbytes = lib.wsage_spmm_workspace_bytes(ctypes.byref(a))
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8) if nbytes else None
@@ -166,5 +183,7 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
         e1.record()
         TIMING.append(dict(algo=int(lib.wsage_spmm_algo(ctypes.byref(a))), n_dst=csr.n_dst, n_src=csr.n_src,
                            nnz=csr.nnz, dim=dim, col_bits=csr.col_bits, self=selfcoef is not None,
+                           dense_nnz=csr.dense.nnz if csr.dense is not None else 0,
+                           dense_pairs=csr.dense.k * csr.dense.t if csr.dense is not None else 0,
                            n_out=int(out is not None) + int(raw is not None), dot=want_dot, events=(e0, e1)))
     return out, raw, dot

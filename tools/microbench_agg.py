@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--dim", type=int, default=400)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--algos", default="1,2")
+    ap.add_argument("--dense", type=float, default=0.0, help="> 0: also time the densified graph (popular genes as a dense block)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     t0 = time.time()
@@ -69,6 +70,21 @@ def main():
             err = float((r1 - r2).abs().max() / r1.abs().max())
             print(name, "gather vs tiled rel err", err, flush=True)
             res[f"{name}/agree"] = err
+    if args.dense > 0:
+        plain = {"cell<-gene": sd.spmm(bg.cell_csr, hg)[0], "gene<-cell": sd.spmm(bg.gene_csr, hc)[0]}
+        t0 = time.time()
+        bg.densify(args.dense, directions=("gene", "cell"))
+        torch.cuda.synchronize()
+        print(f"densify({args.dense}): {len(bg.dense_genes)} genes, {bg.gene_csr.dense.nnz / (bg.gene_csr.nnz + bg.gene_csr.dense.nnz):.3f} "
+              f"of the edges, {time.time()-t0:.1f}s", flush=True)
+        for name, csr, hs, hself in (("cell<-gene", bg.cell_csr, hg, hc), ("gene<-cell", bg.gene_csr, hc, hg)):
+            dscale = torch.rand(csr.n_dst, device=dev) + 0.5
+            selfc = torch.rand(csr.n_dst, device=dev)
+            fn = lambda: sd.spmm(csr, hs, dscale=dscale, selfcoef=selfc, hself=hself)[0]  # noqa: E731
+            best, mean = timed(fn, args.iters, flush)
+            err = float((sd.spmm(csr, hs)[0] - plain[name]).abs().max() / plain[name].abs().max())
+            res[f"{name}/dense{args.dense}"] = dict(ms_best=round(best, 3), ms_mean=round(mean, 3), rel_err_vs_plain=err)
+            print(name, "densified", res[f"{name}/dense{args.dense}"], flush=True)
     print(json.dumps(res))
 
 
