@@ -31,7 +31,7 @@ namespace wsage {
 constexpr int kDenseNW = 12;                       // consumer warps
 constexpr int kDenseTM = 6;                        // destination rows per warp
 constexpr int kDenseT = kDenseNW * kDenseTM;       // destinations per tile (the blocking of xd)
-constexpr int kDenseStages = 3;
+constexpr int kDenseStages = 3;                    // default ring depth (WSAGE_DENSE_STAGES = 2 | 3 | 4 for tuning)
 constexpr int kDenseMaxSplits = 64;
 
 struct DenseParams {
@@ -50,11 +50,11 @@ struct DenseParams {
     float* dout;                // [n_splits][t_total][dim]
 };
 
-template <int DIM>
+template <int DIM, int STG>
 __global__ void __launch_bounds__((kDenseNW + 1) * 32, 1)
 agg_dense_kernel(const DenseParams p) {
     using S = RowShape<DIM>;
-    constexpr int NW = kDenseNW, TM = kDenseTM, T = kDenseT, STG = kDenseStages;
+    constexpr int NW = kDenseNW, TM = kDenseTM, T = kDenseT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STG];
     __shared__ uint64_t empty_bar[STG];
@@ -156,8 +156,17 @@ agg_dense_kernel(const DenseParams p) {
 }
 
 // ------------------------------------------ host side ------------------------------------------
+inline int dense_stages() {
+    static const int v = [] {
+        const char* e = getenv("WSAGE_DENSE_STAGES");
+        const int i = e ? atoi(e) : kDenseStages;
+        return (i >= 2 && i <= 4) ? i : kDenseStages;
+    }();
+    return v;
+}
+
 struct DensePlan {
-    int win_rows, pitch, n_windows, n_tiles, n_splits, win_per_split;
+    int stages, win_rows, pitch, n_windows, n_tiles, n_splits, win_per_split;
     size_t smem_bytes, out_bytes;
 };
 
@@ -167,7 +176,8 @@ inline DensePlan dense_plan(const wsage_spmm_args* a) {
     DensePlan pl{};
     pl.pitch = (a->dim + 31) & ~31;
     const size_t per_row = (size_t)(pl.pitch + kDenseT) * sizeof(float);
-    int w = (int)(kTiledSmemBudget / kDenseStages / per_row);
+    pl.stages = dense_stages();
+    int w = (int)(kTiledSmemBudget / pl.stages / per_row);
     w &= ~1;
     if ((int64_t)w > a->dense_k) w = (int)a->dense_k;
     if (w < 1) w = 1;
@@ -183,19 +193,28 @@ inline DensePlan dense_plan(const wsage_spmm_args* a) {
     if (splits > kDenseMaxSplits) splits = kDenseMaxSplits;
     pl.win_per_split = (pl.n_windows + splits - 1) / splits;
     pl.n_splits = (pl.n_windows + pl.win_per_split - 1) / pl.win_per_split;
-    pl.smem_bytes = (size_t)kDenseStages * w * per_row;
+    pl.smem_bytes = (size_t)pl.stages * w * per_row;
     pl.out_bytes = (size_t)pl.n_splits * a->dense_t * a->dim * sizeof(float);
     pl.out_bytes = (pl.out_bytes + 255) & ~(size_t)255;
     return pl;
 }
 
-template <int DIM>
-int launch_dense_dim(const DenseParams& p, const DensePlan& pl, cudaStream_t st) {
-    auto kern = agg_dense_kernel<DIM>;
+template <int DIM, int STG>
+int launch_dense_shape(const DenseParams& p, const DensePlan& pl, cudaStream_t st) {
+    auto kern = agg_dense_kernel<DIM, STG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_dense)", cudaGetErrorString(e));
     kern<<<pl.n_tiles * pl.n_splits, (kDenseNW + 1) * 32, pl.smem_bytes, st>>>(p);
     return check_launch("agg_dense");
+}
+
+template <int DIM>
+int launch_dense_dim(const DenseParams& p, const DensePlan& pl, cudaStream_t st) {
+    if (DIM == 400) {                      // the bench width carries the tuning variants
+        if (pl.stages == 2) return launch_dense_shape<DIM, 2>(p, pl, st);
+        if (pl.stages == 4) return launch_dense_shape<DIM, 4>(p, pl, st);
+    }
+    return launch_dense_shape<DIM, kDenseStages>(p, pl, st);
 }
 
 // Runs the dense block into `dout` (dense_plan(a).out_bytes bytes of workspace).

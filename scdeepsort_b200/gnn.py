@@ -52,12 +52,19 @@ class _CellAggregate(torch.autograd.Function):
     """neigh_c = s_c·[Σ_g α_g·w_{g→c}·h_g + α_{G+1}·h_c]  for every cell (SURVEY §8a closed form)."""
 
     @staticmethod
-    def forward(ctx, hg, hc, alpha, graph: BipartiteGraph, algo):
+    def forward(ctx, hg, hc, alpha, graph: BipartiteGraph, algo, cells_ready=None):
         g = graph.num_genes
         a = alpha.reshape(-1)
         hs = hg * a[:g, None]                               # α folded into the (small) gene table
-        out, _, _ = ops.spmm(graph.cell_csr, hs, dscale=graph.mean_c * graph.norm_c,
-                             selfcoef=graph.mean_c * a[g + 1], hself=hc, algo=algo)
+        if cells_ready is None:
+            out, _, _ = ops.spmm(graph.cell_csr, hs, dscale=graph.mean_c * graph.norm_c,
+                                 selfcoef=graph.mean_c * a[g + 1], hself=hc, algo=algo)
+        else:
+            # hc is still being copied from the host: the gene->cell sum needs only the gene table, so it runs
+            # under the copy and the self-loop term is added once the rows have landed
+            out, _, _ = ops.spmm(graph.cell_csr, hs, dscale=graph.mean_c * graph.norm_c, algo=algo)
+            torch.cuda.current_stream().wait_event(cells_ready)
+            out.addcmul_(hc, (graph.mean_c * a[g + 1])[:, None])
         ctx.save_for_backward(hg, hc, a)
         ctx.graph, ctx.algo, ctx.alpha_shape = graph, algo, alpha.shape
         return out
@@ -81,7 +88,7 @@ class _CellAggregate(torch.autograd.Function):
             da[:g] = dot
             da[g + 1] = ((hc * dn).sum(dim=1) * graph.mean_c).sum()
             da = da.reshape(ctx.alpha_shape)
-        return dhg, dhc, da, None, None
+        return dhg, dhc, da, None, None, None
 
 
 class _GeneAggregate(torch.autograd.Function):
@@ -167,12 +174,17 @@ class GNN(nn.Module):
         graph = flow.graph
         g, ns = graph.num_genes, graph.num_support
         h = flow.features
+        ready = flow.cells_ready
         for i, layer in enumerate(self.layers):
             if self.dropout:
+                if ready is not None:
+                    torch.cuda.current_stream().wait_event(ready)
+                    ready = None
                 h = self.dropout(h)
             hg, hc = h[:g], h[g:]
             last = i == self.n_layers - 1
-            neigh_c = _CellAggregate.apply(hg, hc, self.alpha, graph, self.spmm_algo)
+            neigh_c = _CellAggregate.apply(hg, hc, self.alpha, graph, self.spmm_algo, ready)
+            ready = None
             if last:
                 if flow.seeds is not None:
                     neigh_c = neigh_c[flow.seeds]

@@ -181,12 +181,17 @@ class FullGraphFlow:
     reference computes for those seeds with full-neighbour NodeFlows, without re-deriving the
     shared lower layers once per 500-seed batch."""
 
-    def __init__(self, graph: BipartiteGraph, features: torch.Tensor, seeds: Optional[torch.Tensor] = None):
+    def __init__(self, graph: BipartiteGraph, features: torch.Tensor, seeds: Optional[torch.Tensor] = None,
+                 cells_ready: Optional[torch.cuda.Event] = None):
         if features.shape[0] != graph.num_genes + graph.num_cells:
             raise ValueError("features must have one row per gene then one per cell")
         self.graph = graph
         self.features = features
         self.seeds = seeds
+        # set by FullGraphTrainer when the CELL rows of ``features`` are still arriving from the host on a
+        # copy stream: the first cell<-gene pass only needs the gene rows, so it runs under the copy and
+        # the event is waited on just before the first read of a cell row
+        self.cells_ready = cells_ready
 
     def layer_parent_nid(self, i):
         if i not in (-1,):

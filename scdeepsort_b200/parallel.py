@@ -87,17 +87,23 @@ class _GenePartial(torch.autograd.Function):
         return dhc, None, None
 
 
-def sharded_forward(model: GNN, graph: BipartiteGraph, features: torch.Tensor) -> torch.Tensor:
-    """GNN.forward on this rank's shard: features = cat[gene rows (replicated); local cell rows]."""
+def sharded_forward(model: GNN, graph: BipartiteGraph, features: torch.Tensor, cells_ready=None) -> torch.Tensor:
+    """GNN.forward on this rank's shard: features = cat[gene rows (replicated); local cell rows].
+    ``cells_ready``: event after which the cell rows of ``features`` are valid (see FullGraphFlow)."""
     g = graph.num_genes
     a = model.alpha.reshape(-1)
     h = features
+    ready = cells_ready
     for i, layer in enumerate(model.layers):
         if model.dropout:
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
+                ready = None
             h = model.dropout(h)
         hg, hc = h[:g], h[g:]
         last = i == model.n_layers - 1
-        neigh_c = _CellAggregate.apply(hg, hc, model.alpha, graph, model.spmm_algo)
+        neigh_c = _CellAggregate.apply(hg, hc, model.alpha, graph, model.spmm_algo, ready)
+        ready = None
         if last:
             h = layer(neigh_c)
         else:

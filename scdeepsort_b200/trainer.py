@@ -152,25 +152,40 @@ class FullGraphTrainer:
         self.optimizer = Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)
         self.sharded = sharded
         self._dev_feat = self._dev_lab = None
+        self._copy_stream = None
 
     def _stage(self, features, labels):
+        """Returns (features, labels, cells_ready) on the device.  Host inputs: the gene rows (small) and the
+        labels are copied on the compute stream; the cell rows (1.2 GB at atlas scale) go H2D on a side
+        stream and ``cells_ready`` marks their arrival, so the first cell<-gene pass — which reads only the
+        gene table — runs under the copy (pinned host memory makes it asynchronous)."""
         if features.is_cuda:
-            return features, labels.to(self.device)
+            return features, labels.to(self.device), None
         if self._dev_feat is None or self._dev_feat.shape != features.shape:
             self._dev_feat = torch.empty(features.shape, dtype=torch.float32, device=self.device)
             self._dev_lab = torch.empty(labels.shape, dtype=torch.int64, device=self.device)
-        self._dev_feat.copy_(features, non_blocking=True)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        g = self.graph.num_genes
+        main = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(main)             # the previous step's kernels are done with the buffer
+        # small copies first: the H2D engine serves requests in issue order, and the compute stream must not
+        # queue behind the 1.2 GB transfer
+        self._dev_feat[:g].copy_(features[:g], non_blocking=True)
         self._dev_lab.copy_(labels, non_blocking=True)
-        return self._dev_feat, self._dev_lab
+        with torch.cuda.stream(self._copy_stream):
+            self._dev_feat[g:].copy_(features[g:], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return self._dev_feat, self._dev_lab, ready
 
     def forward_loss(self, features, labels):
-        feats, lab = self._stage(features, labels)
+        feats, lab, ready = self._stage(features, labels)
         self.model.train()
         if self.sharded:
             from .parallel import sharded_forward
-            logits = sharded_forward(self.model, self.graph, feats)
+            logits = sharded_forward(self.model, self.graph, feats, cells_ready=ready)
         else:
-            logits = self.model(FullGraphFlow(self.graph, feats))
+            logits = self.model(FullGraphFlow(self.graph, feats, cells_ready=ready))
         return cross_entropy_sum(logits, lab), logits
 
     def step(self, features, labels, return_loss=True):

@@ -107,3 +107,24 @@ def test_dense_block_c3_agrees_with_plain_and_checksum():
     lhs = (ah.double() * yc.double()).sum()
     rhs = (hg.double() * sd.spmm(split.gene_csr, yc)[0].double()).sum()
     assert abs(float(lhs - rhs)) < 1e-6 * float(ah.double().norm() * yc.double().norm())
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_full_graph_trainer_host_inputs_match_device_inputs(dense):
+    """FullGraphTrainer.step with pinned HOST tensors (cell rows copied on a side stream under the first
+    cell<-gene pass, self-loop term added after the copy event) == the same steps with device tensors."""
+    from scdeepsort_b200.synthetic import synthetic_features
+    from scdeepsort_b200.trainer import FullGraphTrainer
+    losses = {}
+    for mode in ("device", "host"):
+        bg = synthetic_bipartite(3000, 800, 60, device=DEV)
+        feats = synthetic_features(bg, 128)
+        if dense:
+            bg.densify(0.2)
+        labels = torch.randint(0, 5, (3000,), generator=torch.Generator().manual_seed(1)).to(DEV)
+        tr = FullGraphTrainer(bg, 5, dense_dim=128, hidden_dim=128, n_layers=2, seed=3)
+        f, l = (feats, labels) if mode == "device" else (feats.cpu().pin_memory(), labels.cpu().pin_memory())
+        losses[mode] = [tr.step(f, l) for _ in range(4)]
+    assert losses["device"][0] > 0
+    for a, b in zip(losses["device"], losses["host"]):
+        assert abs(a - b) < 2e-5 * abs(a)
