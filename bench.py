@@ -396,8 +396,25 @@ def run_sampled(a):
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """Everything the libraries print to fd 1 (e.g. c10d's "NCCL version ..." banner) goes to stderr; the
+    returned function writes the ONE JSON line to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real, (line + "\n").encode())
+    return emit
+
+
 if __name__ == "__main__":
     args = parse()
+    _emit = _json_only_stdout()
+    import builtins
+    _print = builtins.print
+    builtins.print = lambda *a, **k: _emit(" ".join(str(x) for x in a)) if not k.get("file") else _print(*a, **k)
     if args.impl == "reference":
         run_reference(args)
     elif args.mode == "sampled":

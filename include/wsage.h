@@ -164,6 +164,17 @@ int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
                     const float* b_hi, const float* b_lo, int64_t ld_b,
                     const float* bias, int32_t relu, float* out, int64_t ld_out,
                     int64_t m, int32_t n, int32_t k, void* stream);
+/* Weight gradient of the same layer (replaces autograd's g^T x through the reference's nn.Linear,
+ * models/gnn.py:13,21):  out[n_out, n_in] = g[rows, n_out]^T * x[rows, n_in], both operands as tf32 hi/lo
+ * pairs from wsage_split_tf32 (row pitches ld_g / ld_x, multiples of 4), n_in <= 512, n_out and n_in
+ * multiples of 4.  The row range is cut into n_splits = wsage_grad_w_splits(rows, n_out) pieces whose
+ * partial products go to `partial` ([n_splits][n_out][n_in] floats, caller-owned) and are added in
+ * split order (deterministic). */
+int wsage_grad_w_splits(int64_t rows, int32_t n_out);
+int wsage_grad_w_tc(const float* g_hi, const float* g_lo, int64_t ld_g,
+                    const float* x_hi, const float* x_lo, int64_t ld_x,
+                    int64_t rows, int32_t n_out, int32_t n_in,
+                    float* partial, int32_t n_splits, float* out, int64_t ld_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * GPU neighbour sampler.  Replaces dgl.contrib.sampling.NeighborSampler's per-hop draw

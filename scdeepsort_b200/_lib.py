@@ -18,7 +18,7 @@ ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
            "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_dense_tile",
-           "wsage_split_tf32", "wsage_linear_tc", "wsage_sample_neighbors",
+           "wsage_split_tf32", "wsage_linear_tc", "wsage_grad_w_splits", "wsage_grad_w_tc", "wsage_sample_neighbors",
            "wsage_softmax_ce", "wsage_adam_step")
 
 
@@ -83,6 +83,11 @@ def load():
     lib.wsage_linear_tc.restype = c_int32
     lib.wsage_linear_tc.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
                                     c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p]
+    lib.wsage_grad_w_splits.restype = c_int32
+    lib.wsage_grad_w_splits.argtypes = [c_int64, c_int32]
+    lib.wsage_grad_w_tc.restype = c_int32
+    lib.wsage_grad_w_tc.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                    c_void_p, c_int32, c_void_p, c_int64, c_void_p]
     lib.wsage_sample_neighbors.restype = c_int32
     lib.wsage_sample_neighbors.argtypes = [c_void_p, c_void_p, c_int64, c_int32, ctypes.c_uint64, c_void_p, c_void_p, c_void_p]
     lib.wsage_softmax_ce.restype = c_int32

@@ -310,4 +310,224 @@ inline int make_tf32_map(CUtensorMap* map, const void* base, int64_t rows, int64
     return WSAGE_OK;
 }
 
+
+// ================================================================================================
+// Weight gradient on the tensor cores:  dW[n_out, n_in] = g[rows, n_out]^T * x[rows, n_in]
+//
+// The reduction runs over the ROWS (all cells and genes, 7.8e5 at atlas scale), so both operands are
+// "MN-major" for the MMA: in memory the M (resp. N) index is contiguous and K strides by a row.  For 32-bit
+// operands the tensor core takes MN-major tiles only in the SWIZZLE_128B_BASE32B layout (CUTLASS sm100_common.inl:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout"): 32 MN elements (128 B) contiguous,
+// K atoms of 4 rows, 32-byte chunks of a row XOR-swizzled by (row mod 4) — which is what a TMA box of
+// [16 k-rows x 32 floats] with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  Descriptor: LBO = 2 KB (next
+// 32-element MN block = next box), SBO = 512 B (next 4-row K atom); one tf32 MMA (K = 8) spans two atoms.
+// Same tf32 hi/lo three-product scheme as linear_tc_kernel.  One CTA per
+// (128-row tile of n_out, split of the row range); partial tiles go to the workspace and
+// grad_w_reduce_kernel adds them in split order (deterministic).
+// ================================================================================================
+constexpr int kGwBlockK = 16;                     // rows (K) per pipeline stage = two 8-row K atoms
+constexpr int kGwMnBlock = 32;                    // floats per swizzle row (128 B)
+constexpr int kGwBoxBytes = kGwBlockK * kGwMnBlock * 4;     // 2 KB: one TMA box = one MN block of a stage
+constexpr int kGwStages = 3;
+constexpr int kGwABlocks = kTcBlockM / kGwMnBlock;          // 4 MN blocks cover the 128-row M tile
+
+struct GradWParams {
+    int64_t rows;            // K extent
+    int n_out, n_in;
+    int n_pad;               // n_in rounded up to 16
+    int n1, n2;              // MMA N halves
+    int b_blocks;            // ceil(n_pad / 32) MN blocks of B per stage
+    int num_kb, kb_per_split, n_splits;
+    float* partial;          // [n_splits][n_out][n_in]
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(const void* smem) {     // MN-major, 128B swizzle with 32B atoms
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)(kGwBoxBytes >> 4) << 16;                   // leading byte offset: next 32-element MN block
+    d |= (uint64_t)(512 >> 4) << 32;                           // stride byte offset: next 4-row K atom
+    d |= (uint64_t)1 << 46;                                    // descriptor version 1 (Blackwell)
+    d |= (uint64_t)1 << 61;                                    // layout type SWIZZLE_128B_BASE32B
+    return d;
+}
+// kind::tf32, D fp32, A and B tf32, both MN-major (bits 15 / 16), M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+}
+
+struct GradWSmem {
+    static __host__ __device__ int a_bytes() { return kGwABlocks * kGwBoxBytes; }                  // 8 KB per hi / lo
+    static __host__ __device__ int b_bytes(int b_blocks) { return b_blocks * kGwBoxBytes; }
+    static __host__ __device__ int stage_bytes(int b_blocks) { return 2 * a_bytes() + 2 * b_bytes(b_blocks); }
+    static __host__ __device__ size_t total(int b_blocks) {
+        return (size_t)kGwStages * stage_bytes(b_blocks) + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
+    }
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+grad_w_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                 const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                 const GradWParams p) {
+    extern __shared__ unsigned char dsmem_raw[];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = GradWSmem::stage_bytes(p.b_blocks);
+    const int a_bytes = GradWSmem::a_bytes();
+    const int b_bytes = GradWSmem::b_bytes(p.b_blocks);
+    float* xpose = reinterpret_cast<float*>(ring + (size_t)kGwStages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xpose + 4 * 32 * 33);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kGwStages;
+    uint64_t* tmem_full = bars + 2 * kGwStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kGwStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles = (p.n_out + kTcBlockM - 1) / kTcBlockM;
+    const int m_tile = blockIdx.x % m_tiles;         // the m tiles of one split are neighbours: they share x in L2
+    const int split = blockIdx.x / m_tiles;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+    const int m0 = m_tile * kTcBlockM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGwStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTcMaxN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x_hi) : "memory");
+            for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+                const int s = it % kGwStages;
+                const uint32_t ph = (it / kGwStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                unsigned char* st = ring + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                const int k0 = kb * kGwBlockK;
+                for (int j = 0; j < kGwABlocks; ++j) {       // blocks past n_out are zero-filled by TMA
+                    tma_load_2d(st + j * kGwBoxBytes, &map_g_hi, m0 + j * kGwMnBlock, k0, &full_bar[s]);
+                    tma_load_2d(st + a_bytes + j * kGwBoxBytes, &map_g_lo, m0 + j * kGwMnBlock, k0, &full_bar[s]);
+                }
+                unsigned char* sb = st + 2 * a_bytes;
+                for (int j = 0; j < p.b_blocks; ++j) {
+                    tma_load_2d(sb + j * kGwBoxBytes, &map_x_hi, j * kGwMnBlock, k0, &full_bar[s]);
+                    tma_load_2d(sb + b_bytes + j * kGwBoxBytes, &map_x_lo, j * kGwMnBlock, k0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc_tf32_mn(p.n1);
+            const uint32_t idesc2 = umma_idesc_tf32_mn(p.n2 > 0 ? p.n2 : 16);
+            for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+                const int s = it % kGwStages;
+                const uint32_t ph = (it / kGwStages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                unsigned char* st = ring + (size_t)s * stage_bytes;
+                const uint64_t a_hi = umma_desc_mn_sw128(st), a_lo = umma_desc_mn_sw128(st + a_bytes);
+                unsigned char* sb = st + 2 * a_bytes;
+                const uint64_t b_hi = umma_desc_mn_sw128(sb), b_lo = umma_desc_mn_sw128(sb + b_bytes);
+                const uint64_t n2_off = (uint64_t)(((p.n1 / kGwMnBlock) * kGwBoxBytes) >> 4);     // n1 = 256 -> 8 MN blocks
+#pragma unroll
+                for (int kk = 0; kk < kGwBlockK / kTcUmmaK; ++kk) {          // one 8-row K atom (1 KB) per MMA
+                    const uint64_t ko = (uint64_t)((kk * 1024) >> 4);
+                    const uint32_t acc0 = (it | kk) != 0;
+                    tc_mma_tf32(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
+                    tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
+                    tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                    if (p.n2 > 0) {
+                        tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
+                        tc_mma_tf32(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
+                        tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                    }
+                }
+                tc_commit(&empty_bar[s]);
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        float* xp = xpose + (warp - 2) * 32 * 33;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row0 = m0 + q * 32;
+        float* dst = p.partial + (size_t)split * p.n_out * p.n_in;
+        for (int c0 = 0; c0 < p.n_in; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = v[j];
+            __syncwarp();
+            const int c = c0 + lane;
+            if (c < p.n_in) {
+                for (int r = 0; r < 32; ++r) {
+                    const int row = row0 + r;
+                    if (row >= p.n_out) break;
+                    dst[(size_t)row * p.n_in + c] = xp[r * 33 + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcMaxN));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grad_w_reduce_kernel(const float* __restrict__ partial, int n_splits, int64_t n, float* __restrict__ out, int64_t ld_out, int n_in) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < n_splits; ++k) s += partial[(size_t)k * n + i];
+        out[(i / n_in) * ld_out + (i % n_in)] = s;
+    }
+}
+
+// fp32 (tf32-valued) matrix [rows, cols], row pitch ld: box = [16 rows, 32 cols], 128-byte swizzle (MN-major operand).
+inline int make_tf32_mn_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(WSAGE_ECUDA, "%s: %s", "wsage_grad_w_tc", "cuTensorMapEncodeTiled not available");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kGwMnBlock, (cuuint32_t)kGwBlockK};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WSAGE_ECUDA, "%s: %s", "wsage_grad_w_tc", "cuTensorMapEncodeTiled failed");
+    return WSAGE_OK;
+}
+
+// The tensor core adds into its fp32 accumulator with truncation, so the error of one accumulation chain
+// grows linearly with its length (measured: ~7e-9 relative per row, 1.5e-4 at 21k rows, 3e-6 at 400).  A CTA
+// therefore never accumulates more than kGwMaxChainKb k-blocks (1024 rows); the partial tiles are added in
+// fp32 round-to-nearest by grad_w_reduce_kernel.
+constexpr int kGwMaxChainKb = 64;
+
+inline int grad_w_splits(int64_t rows, int n_out) {
+    const int m_tiles = (n_out + kTcBlockM - 1) / kTcBlockM;
+    const int64_t num_kb = (rows + kGwBlockK - 1) / kGwBlockK;
+    int64_t splits = kNumSMs / m_tiles;
+    if (splits > num_kb / 32) splits = num_kb / 32;        // at least 32 k-blocks (512 rows) per CTA when filling the chip
+    const int64_t prec = (num_kb + kGwMaxChainKb - 1) / kGwMaxChainKb;
+    if (splits < prec) splits = prec;
+    if (splits < 1) splits = 1;
+    return (int)splits;
+}
+
 }  // namespace wsage

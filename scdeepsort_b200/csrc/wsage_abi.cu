@@ -209,6 +209,57 @@ int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
     return check_launch("linear_tc");
 }
 
+int wsage_grad_w_splits(int64_t rows, int32_t n_out) {
+    if (rows <= 0 || n_out <= 0) return 0;
+    const int s = grad_w_splits(rows, n_out);
+    const int64_t num_kb = (rows + kGwBlockK - 1) / kGwBlockK;
+    const int64_t per = (num_kb + s - 1) / s;
+    return (int)((num_kb + per - 1) / per);             // every split owns at least one k-block
+}
+
+int wsage_grad_w_tc(const float* g_hi, const float* g_lo, int64_t ld_g,
+                    const float* x_hi, const float* x_lo, int64_t ld_x,
+                    int64_t rows, int32_t n_out, int32_t n_in,
+                    float* partial, int32_t n_splits, float* out, int64_t ld_out, void* stream) {
+    WSAGE_REQUIRE(rows > 0 && n_out > 0 && n_in > 0, "bad shape");
+    WSAGE_REQUIRE(g_hi && g_lo && x_hi && x_lo && partial && out, "null pointer");
+    WSAGE_REQUIRE(n_out % 4 == 0 && n_in % 4 == 0, "n_out and n_in must be multiples of 4");
+    const int n_pad = (n_in + 15) & ~15;
+    WSAGE_REQUIRE(n_pad <= kTcMaxN, "n_in must be <= 512");
+    WSAGE_REQUIRE(ld_g >= n_out && ld_x >= n_in && ld_g % 4 == 0 && ld_x % 4 == 0 && ld_out >= n_in, "bad leading dimension");
+    WSAGE_REQUIRE(aligned16(g_hi) && aligned16(g_lo) && aligned16(x_hi) && aligned16(x_lo), "operands must be 16-byte aligned");
+    WSAGE_REQUIRE(rows < ((int64_t)1 << 31) - kGwBlockK, "too many rows");
+    WSAGE_REQUIRE(n_splits == wsage_grad_w_splits(rows, n_out), "n_splits must come from wsage_grad_w_splits");
+    GradWParams p{};
+    p.rows = rows; p.n_out = n_out; p.n_in = n_in; p.n_pad = n_pad;
+    p.n1 = n_pad < 256 ? n_pad : 256;
+    p.n2 = n_pad - p.n1;
+    p.b_blocks = (n_pad + kGwMnBlock - 1) / kGwMnBlock;
+    p.num_kb = (int)((rows + kGwBlockK - 1) / kGwBlockK);
+    p.n_splits = n_splits;
+    p.kb_per_split = (p.num_kb + n_splits - 1) / n_splits;
+    p.partial = partial;
+    const size_t smem = GradWSmem::total(p.b_blocks);
+    if (smem > 227 * 1024)
+        return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_grad_w_tc", "n_in too large for the 3-stage shared-memory ring");
+    CUtensorMap mg_hi, mg_lo, mx_hi, mx_lo;
+    int rc;
+    if ((rc = make_tf32_mn_map(&mg_hi, g_hi, rows, n_out, ld_g)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_mn_map(&mg_lo, g_lo, rows, n_out, ld_g)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_mn_map(&mx_hi, x_hi, rows, n_in, ld_x)) != WSAGE_OK) return rc;
+    if ((rc = make_tf32_mn_map(&mx_lo, x_lo, rows, n_in, ld_x)) != WSAGE_OK) return rc;
+    cudaError_t e = cudaFuncSetAttribute(grad_w_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(grad_w_tc)", cudaGetErrorString(e));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int m_tiles = (n_out + kTcBlockM - 1) / kTcBlockM;
+    grad_w_tc_kernel<<<m_tiles * n_splits, kTcThreads, smem, st>>>(mg_hi, mg_lo, mx_hi, mx_lo, p);
+    rc = check_launch("grad_w_tc");
+    if (rc != WSAGE_OK) return rc;
+    const int64_t n = (int64_t)n_out * n_in;
+    grad_w_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(partial, n_splits, n, out, ld_out, n_in);
+    return check_launch("grad_w_reduce");
+}
+
 int wsage_sample_neighbors(const int64_t* rowptr, const int64_t* nodes, int64_t n_nodes,
                            int32_t fanout, uint64_t seed, int64_t* out_eid, int32_t* out_deg,
                            void* stream) {

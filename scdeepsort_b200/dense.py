@@ -31,6 +31,7 @@ def split_tf32(x: torch.Tensor, mask_src: torch.Tensor = None, want_masked=False
 
 
 _MAX_N = 512      # TMEM columns of one CTA: wider outputs are produced in column blocks
+use_tc_grad_w = True     # weight gradient on the tensor cores (wsage_grad_w_tc); False: torch (cuBLAS fp32)
 
 
 def linear_tc(a_hi, a_lo, b_hi, b_lo, m, n, k, bias=None, relu=False):
@@ -46,6 +47,25 @@ def linear_tc(a_hi, a_lo, b_hi, b_lo, m, n, k, bias=None, relu=False):
                                        _ptr(bias[n0:]) if bias is not None else None, 1 if relu else 0,
                                        _ptr(o), out.stride(0), m, nc, k, _stream()), "wsage_linear_tc")
     return out
+
+
+def grad_w_tc(g_hi, g_lo, x_hi, x_lo):
+    """dW[n_out, n_in] = g^T x on the tensor cores (MN-major tf32 hi/lo operands, reduction over the rows)."""
+    rows, n_out = g_hi.shape
+    n_in = x_hi.shape[1]
+    lib = _lib.load()
+    splits = int(lib.wsage_grad_w_splits(rows, n_out))
+    partial = torch.empty(splits, n_out, n_in, device=g_hi.device, dtype=torch.float32)
+    out = torch.empty(n_out, n_in, device=g_hi.device, dtype=torch.float32)
+    _lib.check(lib.wsage_grad_w_tc(_ptr(g_hi), _ptr(g_lo), g_hi.stride(0), _ptr(x_hi), _ptr(x_lo), x_hi.stride(0),
+                                   rows, n_out, n_in, _ptr(partial), splits, _ptr(out), out.stride(0), _stream()),
+               "wsage_grad_w_tc")
+    return out
+
+
+def grad_w_supported(rows: int, n_out: int, n_in: int) -> bool:
+    # n_in <= 416: thirteen 32-column blocks of x per stage is what the 3-stage shared-memory ring holds
+    return rows > 0 and n_out % 4 == 0 and n_in % 4 == 0 and 0 < n_in <= 416 and n_out > 0
 
 
 def tc_supported(in_features: int, out_features: int) -> bool:
@@ -64,13 +84,18 @@ class _LinearReluTC(torch.autograd.Function):
         x_hi, x_lo, _ = split_tf32(x)
         w_hi, w_lo, _ = split_tf32(weight.contiguous())
         y = linear_tc(x_hi, x_lo, w_hi, w_lo, m, n, k, bias=bias, relu=relu)
-        ctx.save_for_backward(x, weight, y if relu else None)
+        # the weight gradient consumes the split input again (as the MN-major operand of g^T x)
+        ctx.tc_dw = use_tc_grad_w and grad_w_supported(m, n, k)
+        if ctx.tc_dw:
+            ctx.save_for_backward(x_hi, x_lo, weight, y if relu else None)
+        else:
+            ctx.save_for_backward(x, None, weight, y if relu else None)
         ctx.relu = relu
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        x, x_lo, weight, y = ctx.saved_tensors          # x is x_hi when ctx.tc_dw
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
         dy = dy.contiguous()
         m, n = dy.shape
@@ -84,7 +109,7 @@ class _LinearReluTC(torch.autograd.Function):
             wt_hi, wt_lo, _ = split_tf32(weight.t().contiguous())          # B = W^T : [K, N], reduction over N
             dx = linear_tc(g_hi, g_lo, wt_hi, wt_lo, m, k, n)
         if need_w:
-            dw = g.t() @ x
+            dw = grad_w_tc(g_hi, g_lo, x, x_lo) if ctx.tc_dw else g.t() @ x
         if need_b:
             db = g.sum(dim=0)
         return dx, dw, db, None

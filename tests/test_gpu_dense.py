@@ -67,3 +67,19 @@ def test_unsupported_shapes_are_rejected():
     p = lambda t: ctypes.c_void_p(t.data_ptr())     # noqa: E731
     rc = lib.wsage_linear_tc(p(a), p(a), 48, p(b), p(b), 48, None, 0, p(o), 520, 8, 520, 48, None)
     assert rc == sd._lib.EINVAL and b"512" in lib.wsage_last_error()    # the raw ABI call takes N <= 512
+
+
+@pytest.mark.parametrize("rows,n_out,n_in", [(5000, 400, 400), (777, 16, 400), (3001, 200, 400), (3000, 400, 200),
+                                             (150000, 400, 400), (40, 8, 32), (20000, 132, 260), (15, 512, 416)])
+def test_grad_w_tc_matches_fp64(rows, n_out, n_in):
+    """wsage_grad_w_tc: dW = g^T x with MN-major tf32 hi/lo operands, split over the rows, vs fp64."""
+    gen = torch.Generator(device="cpu").manual_seed(rows + n_out + n_in)
+    g = torch.randn(rows, n_out, generator=gen).to(DEV)
+    x = torch.randn(rows, n_in, generator=gen).to(DEV)
+    g_hi, g_lo, _ = dense.split_tf32(g)
+    x_hi, x_lo, _ = dense.split_tf32(x)
+    assert dense.grad_w_supported(rows, n_out, n_in)
+    dw = dense.grad_w_tc(g_hi, g_lo, x_hi, x_lo)
+    ref = g.double().t() @ x.double()
+    assert rel_err(dw.cpu(), ref.cpu()) < 1.5e-5      # chains of <= 1024 rows: ~7e-6 from the truncating accumulator
+    assert torch.equal(dw, dense.grad_w_tc(g_hi, g_lo, x_hi, x_lo))          # split partials added in fixed order
