@@ -56,6 +56,8 @@ struct TiledParams {
     int win_per_split;
     const int32_t* row_perm;
     int l2_prefetch;          // > 0: some CTAs prefetch the window this many windows ahead into L2
+    int diag;                 // profiling aid (WSAGE_TILED_DIAG): 1 = producer copies nothing (consumer-side time only,
+                              // results meaningless), 2 = consumers skip the edge walk (fill-side time only)
     // accumulators start from the dense block's sums (agg_dense.cuh): init[slab][slot][dim], slabs added in
     // index order by the split-0 CTA of the row; slot = init_map[row] (< 0: none) or the row itself
     const float* init;
@@ -225,6 +227,10 @@ agg_tiled_kernel(const TiledParams p) {
                 const int prows = (int)min((int64_t)p.win_rows, p.n_src - prow0);
                 bulk_prefetch_l2(p.hs + prow0 * dim, prows * row_bytes);
             }
+            if (p.diag == 1) {
+                if (lane == 0) mbar_arrive(&full_bar[s]);
+                continue;
+            }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes);
             __syncwarp();
             for (int r = lane; r < rows; r += 32)
@@ -333,6 +339,11 @@ agg_tiled_kernel(const TiledParams p) {
         const int win_end = win_base + p.win_rows;
         const float* stage = stages + s * stage_floats + lane * 4 - (size_t)win_base * pitch;
         mbar_wait(&full_bar[s], ph);
+        if (p.diag == 2) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            continue;
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             while (true) {
@@ -536,6 +547,8 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const Tile
     {   // WSAGE_TILED_L2PF (env, tuning only): prefetch distance in windows
         static const int forced = [] { const char* e = getenv("WSAGE_TILED_L2PF"); return e ? atoi(e) : -1; }();
         const bool big = (double)a->n_src * a->dim * sizeof(float) > 64.0 * (1 << 20);
+        static const int diag = [] { const char* e = getenv("WSAGE_TILED_DIAG"); return e ? atoi(e) : 0; }();
+        p.diag = diag;
         p.l2_prefetch = forced >= 0 ? forced : 0;      // measured: no gain at c3/c4 (the slice is L2-resident), off
         (void)big;
     }
