@@ -38,6 +38,7 @@ constexpr int kTiledStages = 4;                // deepest window ring among the 
 constexpr int kTiledSmemBudget = 224 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
 constexpr int kTiledNW = 12;                   // consumer warps per CTA
 constexpr int kTiledR = 4;                     // destination rows per warp
+constexpr int kTiledDefaultCluster = 1;        // CTAs per cluster sharing window loads (WSAGE_TILED_CLUSTER overrides)
 
 struct TiledParams {
     const int64_t* rowptr;
@@ -110,6 +111,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// --- thread-block-cluster helpers (CL = 2: two CTAs on neighbouring SMs share every window load) -----------
+// The same bulk copy, written into the shared memory of every CTA in cta_mask at the same offset; each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {     // arrive on the peer CTA's barrier
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta_rank) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // How a DIM-float row is spread over the 32 lanes of a warp.
 template <int DIM>
 struct RowShape {
@@ -174,12 +192,16 @@ __device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t
     }
 }
 
-template <typename ColT, int DIM, int NW, int R, int STG, bool ESM>
+template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1>
 // one CTA per SM; ptxas derives the register cap from the warp count (16K registers per SM sub-partition,
-// so 13 warps -> 128 registers/thread, 12 warps -> 168)
+// so 13 warps -> 128 registers/thread, 12 warps -> 168).
+// CL = 2: launched as clusters of two CTAs (neighbouring tiles of the same split).  Each producer copies every
+// other row of the window and multicasts it into both CTAs' rings, so L2 and the crossbar deliver every source
+// row once per PAIR of tiles; a stage is refilled only after the consumers of BOTH CTAs have released it.
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 agg_tiled_kernel(const TiledParams p) {
     using S = RowShape<DIM>;
+    const uint32_t cta_rank = CL > 1 ? (blockIdx.x % CL) : 0;
     constexpr int kTiledStages = STG;       // depth of the window ring
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STG];
@@ -204,11 +226,11 @@ agg_tiled_kernel(const TiledParams p) {
 #pragma unroll
         for (int s = 0; s < kTiledStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], NW);
+            mbar_init(&empty_bar[s], NW * CL);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();       // peers must not touch uninitialised barriers
 
     if (warp == NW) {
         // ------------------------------- producer -------------------------------------------
@@ -231,11 +253,18 @@ agg_tiled_kernel(const TiledParams p) {
                 if (lane == 0) mbar_arrive(&full_bar[s]);
                 continue;
             }
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes);
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes);     // bytes of BOTH producers land here
             __syncwarp();
-            for (int r = lane; r < rows; r += 32)
-                bulk_g2s(stages + s * stage_floats + (size_t)r * pitch, p.hs + (row0 + r) * dim, row_bytes, &full_bar[s]);
+            if (CL > 1) {
+                for (int r = lane * CL + (int)cta_rank; r < rows; r += 32 * CL)
+                    bulk_g2s_multicast(stages + s * stage_floats + (size_t)r * pitch, p.hs + (row0 + r) * dim, row_bytes,
+                                       &full_bar[s], (uint16_t)((1u << CL) - 1));
+            } else {
+                for (int r = lane; r < rows; r += 32)
+                    bulk_g2s(stages + s * stage_floats + (size_t)r * pitch, p.hs + (row0 + r) * dim, row_bytes, &full_bar[s]);
+            }
         }
+        if (CL > 1) cluster_sync_all();      // stay resident while the peer may still write into this CTA
         return;
     }
 
@@ -341,7 +370,10 @@ agg_tiled_kernel(const TiledParams p) {
         mbar_wait(&full_bar[s], ph);
         if (p.diag == 2) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) {
+                mbar_arrive(&empty_bar[s]);
+                if (CL > 1) mbar_arrive_remote(&empty_bar[s], cta_rank ^ 1);
+            }
             continue;
         }
 #pragma unroll
@@ -407,8 +439,13 @@ agg_tiled_kernel(const TiledParams p) {
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) {
+            mbar_arrive(&empty_bar[s]);
+            if (CL > 1) mbar_arrive_remote(&empty_bar[s], cta_rank ^ 1);
+        }
     }
+
+    if (CL > 1) cluster_sync_all();      // the peer may still multicast into / arrive on this CTA until its last window
 
     // ------------------------------------ epilogue -------------------------------------------
 #pragma unroll
@@ -536,7 +573,12 @@ inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
 
 struct TiledInit { const float* init; int slabs; int64_t rows; const int32_t* map; };
 
-template <typename ColT, int DIM, int NW, int R, int STG, bool ESM>
+inline int tiled_cluster() {      // WSAGE_TILED_CLUSTER = 1 | 2 (dim 400 default shape only)
+    static const int v = [] { const char* e = getenv("WSAGE_TILED_CLUSTER"); const int i = e ? atoi(e) : kTiledDefaultCluster; return i == 2 ? 2 : 1; }();
+    return v;
+}
+
+template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1>
 int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const TiledInit& ini, cudaStream_t st) {
     TiledParams p{};
     p.init = ini.init; p.init_slabs = ini.slabs; p.init_rows = ini.rows; p.init_map = ini.map;
@@ -556,10 +598,27 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const Tile
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
     p.partial = static_cast<float*>(a->workspace);
-    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG, ESM>;
+    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG, ESM, CL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_tiled)", cudaGetErrorString(e));
-    kern<<<pl.n_tiles * pl.n_splits, (NW + 1) * 32, pl.smem_bytes, st>>>(p);
+    if (CL > 1) {
+        // clusters pair neighbouring tiles of one split: pad the tile count to a multiple of CL (the extra tile has
+        // no rows but takes part in the ring protocol)
+        p.n_tiles = (pl.n_tiles + CL - 1) / CL * CL;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.n_tiles * pl.n_splits));
+        cfg.blockDim = dim3((NW + 1) * 32);
+        cfg.dynamicSmemBytes = pl.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, p);
+        if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaLaunchKernelEx(agg_tiled cluster)", cudaGetErrorString(e));
+    } else {
+        kern<<<pl.n_tiles * pl.n_splits, (NW + 1) * 32, pl.smem_bytes, st>>>(p);
+    }
     int rc = check_launch("agg_tiled");
     if (rc != WSAGE_OK || pl.n_splits == 1) return rc;
     tiled_reduce_kernel<<<gather_grid(a->n_dst), 256, 0, st>>>(p);
@@ -575,7 +634,9 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledI
                 case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4, true>(a, pl, ini, st);
                 case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, ini, st);
                 case 4: return launch_tiled_shape<ColT, 400, 12, 4, 2, true>(a, pl, ini, st);
-                default: return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, ini, st);
+                default:
+                    if (tiled_cluster() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 2>(a, pl, ini, st);
+                    return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, ini, st);
             }
         case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3, true>(a, pl, ini, st);
         case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3, true>(a, pl, ini, st);
