@@ -57,8 +57,6 @@ struct TiledParams {
     int win_per_split;
     const int32_t* row_perm;
     int l2_prefetch;          // > 0: some CTAs prefetch the window this many windows ahead into L2
-    int diag;                 // profiling aid (WSAGE_TILED_DIAG): 1 = producer copies nothing (consumer-side time only,
-                              // results meaningless), 2 = consumers skip the edge walk (fill-side time only)
     // accumulators start from the dense block's sums (agg_dense.cuh): init[slab][slot][dim], slabs added in
     // index order by the split-0 CTA of the row; slot = init_map[row] (< 0: none) or the row itself
     const float* init;
@@ -94,6 +92,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Same, on precomputed 32-bit shared-window addresses (keeps the generic->shared conversion out of hot loops).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -192,7 +203,7 @@ __device__ __forceinline__ void tiled_row_epilogue(const TiledParams& p, int64_t
     }
 }
 
-template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1>
+template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1, int DIAG = 0>
 // one CTA per SM; ptxas derives the register cap from the warp count (16K registers per SM sub-partition,
 // so 13 warps -> 128 registers/thread, 12 warps -> 168).
 // CL = 2: launched as clusters of two CTAs (neighbouring tiles of the same split).  Each producer copies every
@@ -249,7 +260,7 @@ agg_tiled_kernel(const TiledParams p) {
                 const int prows = (int)min((int64_t)p.win_rows, p.n_src - prow0);
                 bulk_prefetch_l2(p.hs + prow0 * dim, prows * row_bytes);
             }
-            if (p.diag == 1) {
+            if (DIAG == 1) {
                 if (lane == 0) mbar_arrive(&full_bar[s]);
                 continue;
             }
@@ -361,19 +372,24 @@ agg_tiled_kernel(const TiledParams p) {
         publish(r);
     }
 
-    for (int w = w_begin, it = 0; w < w_end; ++w, ++it) {
-        const int s = it % kTiledStages;
-        const uint32_t ph = (it / kTiledStages) & 1;
-        const int win_base = w * p.win_rows;
-        const int win_end = win_base + p.win_rows;
-        const float* stage = stages + s * stage_floats + lane * 4 - (size_t)win_base * pitch;
-        mbar_wait(&full_bar[s], ph);
-        if (p.diag == 2) {
+    // Per-window bookkeeping is kept off the critical path after the barrier: stage index, phase, window bounds and
+    // the stage pointer are running values (the pointer of window w in slot s is stages + (s - w)·W·pitch, which
+    // only changes when the ring wraps), barrier addresses are precomputed shared-window offsets.
+    const uint32_t full_a0 = smem_u32(&full_bar[0]), empty_a0 = smem_u32(&empty_bar[0]);
+    int s = 0;
+    uint32_t ph = 0;
+    int win_end = w_begin * p.win_rows;
+    const float* stage = stages + lane * 4 - (size_t)win_end * pitch;
+    for (int w = w_begin; w < w_end; ++w) {
+        win_end += p.win_rows;
+        mbar_wait_a(full_a0 + 8u * s, ph);
+        if (DIAG == 2) {
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&empty_bar[s]);
+                mbar_arrive_a(empty_a0 + 8u * s);
                 if (CL > 1) mbar_arrive_remote(&empty_bar[s], cta_rank ^ 1);
             }
+            if (++s == kTiledStages) { s = 0; ph ^= 1; stage -= (size_t)kTiledStages * stage_floats; }
             continue;
         }
 #pragma unroll
@@ -440,9 +456,10 @@ agg_tiled_kernel(const TiledParams p) {
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&empty_bar[s]);
+            mbar_arrive_a(empty_a0 + 8u * s);
             if (CL > 1) mbar_arrive_remote(&empty_bar[s], cta_rank ^ 1);
         }
+        if (++s == kTiledStages) { s = 0; ph ^= 1; stage -= (size_t)kTiledStages * stage_floats; }
     }
 
     if (CL > 1) cluster_sync_all();      // the peer may still multicast into / arrive on this CTA until its last window
@@ -573,12 +590,20 @@ inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
 
 struct TiledInit { const float* init; int slabs; int64_t rows; const int32_t* map; };
 
+// Profiling aid (WSAGE_TILED_DIAG, dim 400 default shape only; compile-time variants so that the production kernel
+// carries no extra branch — a run-time flag in the window loop cost 3.7 % of the step): 1 = the producer copies
+// nothing (edge-walk time only, results meaningless), 2 = the consumers skip the edge walk (window-fill time only).
+inline int tiled_diag() {
+    static const int v = [] { const char* e = getenv("WSAGE_TILED_DIAG"); const int i = e ? atoi(e) : 0; return (i == 1 || i == 2) ? i : 0; }();
+    return v;
+}
+
 inline int tiled_cluster() {      // WSAGE_TILED_CLUSTER = 1 | 2 (dim 400 default shape only)
     static const int v = [] { const char* e = getenv("WSAGE_TILED_CLUSTER"); const int i = e ? atoi(e) : kTiledDefaultCluster; return i == 2 ? 2 : 1; }();
     return v;
 }
 
-template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1>
+template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1, int DIAG = 0>
 int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const TiledInit& ini, cudaStream_t st) {
     TiledParams p{};
     p.init = ini.init; p.init_slabs = ini.slabs; p.init_rows = ini.rows; p.init_map = ini.map;
@@ -589,8 +614,6 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const Tile
     {   // WSAGE_TILED_L2PF (env, tuning only): prefetch distance in windows
         static const int forced = [] { const char* e = getenv("WSAGE_TILED_L2PF"); return e ? atoi(e) : -1; }();
         const bool big = (double)a->n_src * a->dim * sizeof(float) > 64.0 * (1 << 20);
-        static const int diag = [] { const char* e = getenv("WSAGE_TILED_DIAG"); return e ? atoi(e) : 0; }();
-        p.diag = diag;
         p.l2_prefetch = forced >= 0 ? forced : 0;      // measured: no gain at c3/c4 (the slice is L2-resident), off
         (void)big;
     }
@@ -598,7 +621,7 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const Tile
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
     p.partial = static_cast<float*>(a->workspace);
-    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG, ESM, CL>;
+    auto kern = agg_tiled_kernel<ColT, DIM, NW, R, STG, ESM, CL, DIAG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(agg_tiled)", cudaGetErrorString(e));
     if (CL > 1) {
@@ -635,6 +658,8 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledI
                 case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, ini, st);
                 case 4: return launch_tiled_shape<ColT, 400, 12, 4, 2, true>(a, pl, ini, st);
                 default:
+                    if (tiled_diag() == 1) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 1>(a, pl, ini, st);
+                    if (tiled_diag() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 2>(a, pl, ini, st);
                     if (tiled_cluster() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 2>(a, pl, ini, st);
                     return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, ini, st);
             }

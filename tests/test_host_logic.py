@@ -196,3 +196,47 @@ def test_product_never_imports_the_oracle():
     gpu_arm = bench[bench.index("def run_ours"):bench.index("def run_sampled")]
     # the only oracle use inside run_ours is the bounded cpu_baseline leg (cpu_reference_steps)
     assert "from oracle" not in gpu_arm and gpu_arm.count("cpu_reference_steps(") == 1
+
+
+def test_densify_splits_expression_matrix_exactly():
+    """BipartiteGraph.densify: CSR remainder + dense block reproduce the expression matrix bit for bit in both
+    directions (host tensors; the kernels that consume the block are covered by tests/test_gpu_dense_block.py)."""
+    import scipy.sparse as sp
+    from scdeepsort_b200.graph import BipartiteGraph
+    rng = np.random.RandomState(0)
+    c, g = 300, 150
+    pop = np.minimum(1, 3 * np.arange(1, g + 1) ** -0.8)[rng.permutation(g)]
+    mask = rng.rand(c, g) < pop[None, :]
+    x = sp.csr_matrix(np.where(mask, rng.rand(c, g) + 0.1, 0).astype(np.float32))
+    full = x.toarray()
+    tile = sd._lib.load().wsage_dense_tile()
+
+    def rebuild(csr, side):
+        col = csr.col.to(torch.int64)
+        if csr.col_bits == 16:
+            col = col & 0xFFFF
+        a = sp.csr_matrix((csr.x.numpy(), col.numpy(), csr.rowptr.numpy()), shape=(csr.n_dst, csr.n_src)).toarray()
+        d = csr.dense
+        nt = (d.t + tile - 1) // tile
+        xd = d.x.view(nt, d.k, tile).permute(1, 0, 2).reshape(d.k, nt * tile)[:, :d.t].numpy()      # [source, slot]
+        if side == "src":
+            a[:, d.src_ids.numpy()] += xd.T
+        else:
+            slots = d.dst_map.numpy()
+            rows = np.nonzero(slots >= 0)[0]
+            a[rows, :] += xd[:, slots[rows]].T
+        return a
+
+    bg = BipartiteGraph.from_expression(x).densify(0.2, directions=("gene", "cell"))
+    assert bg.densified and 0 < len(bg.dense_genes) < g
+    assert bg.cell_csr.nnz + bg.cell_csr.dense.nnz == x.nnz == bg.nnz
+    assert np.array_equal(rebuild(bg.cell_csr, "src"), full)
+    assert np.array_equal(rebuild(bg.gene_csr, "dst"), full.T)
+    # columns stay sorted inside every remaining row; the default touches the gene-destination CSR only
+    rp, col = bg.gene_csr.rowptr.numpy(), (bg.gene_csr.col.to(torch.int64) & 0xFFFF).numpy()
+    assert all(np.all(np.diff(col[rp[i]:rp[i + 1]]) > 0) for i in range(g))
+    bg2 = BipartiteGraph.from_expression(x).densify(0.2)
+    assert bg2.cell_csr.dense is None and bg2.gene_csr.dense is not None
+    # nothing popular enough: unchanged
+    bg3 = BipartiteGraph.from_expression(x).densify(1.1)
+    assert not getattr(bg3, "densified", False) and bg3.gene_csr.dense is None
