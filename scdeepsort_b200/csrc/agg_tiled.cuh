@@ -376,6 +376,10 @@ agg_tiled_kernel(const TiledParams p) {
     // the stage pointer are running values (the pointer of window w in slot s is stages + (s - w)·W·pitch, which
     // only changes when the ring wraps), barrier addresses are precomputed shared-window offsets.
     const uint32_t full_a0 = smem_u32(&full_bar[0]), empty_a0 = smem_u32(&empty_bar[0]);
+    // scalar tail chunk (columns J4*128 + lane): when the padded row has room for 32 lanes (400 -> pitch 416) every
+    // lane loads, lanes past the row read the never-written padding into an accumulator that is never stored —
+    // same single wavefront, no predicate / zero-fill instructions in the hot loop
+    constexpr bool kTailAllLanes = DIM > 0 && S::TAIL1 && (((DIM + 31) & ~31) - S::J4 * 128 >= 32);
     int s = 0;
     uint32_t ph = 0;
     int win_end = w_begin * p.win_rows;
@@ -415,7 +419,7 @@ agg_tiled_kernel(const TiledParams p) {
                             b4[j] = *reinterpret_cast<const float4*>(s1 + j * 128);
                         }
                     }
-                    if (S::TAIL1 && S::on1(lane)) {
+                    if (S::TAIL1 && (kTailAllLanes || S::on1(lane))) {
                         a1 = s0[S::J4 * 128 - lane * 3];           // column J4*128 + lane (s0 already has +4*lane)
                         b1 = s1[S::J4 * 128 - lane * 3];
                     }
@@ -438,7 +442,7 @@ agg_tiled_kernel(const TiledParams p) {
 #pragma unroll
                     for (int j = 0; j < S::N4; ++j)
                         if (S::on4(j, lane, dim)) a4[j] = *reinterpret_cast<const float4*>(s0 + j * 128);
-                    if (S::TAIL1 && S::on1(lane)) a1 = s0[S::J4 * 128 - lane * 3];
+                    if (S::TAIL1 && (kTailAllLanes || S::on1(lane))) a1 = s0[S::J4 * 128 - lane * 3];
 #pragma unroll
                     for (int j = 0; j < S::N4; ++j)
                         if (S::on4(j, lane, dim)) Vec<4>::fma(acc[r].v4[j], x0, a4[j]);
