@@ -262,17 +262,25 @@ def run_ours(a):
                     "gather_side_tbs": g["gather_bytes"] / g["ms"] / 1e9,
                     "note": "algorithmic bytes count distinct rows once (SURVEY 8d); the E*D gather is served "
                             "on-chip (L2/L1/smem), reported as gather_side_tbs and bounded by onchip"}
-        if key[0] == "tiled":
-            # the resource that actually binds this kernel: the LSU / shared-memory data pipe, 1 wavefront (128 B)
-            # per clock per SM; per edge the kernel issues ceil(row bytes / 128) LDS wavefronts for the source
-            # row + 1 broadcast LDS.64 for the edge's (column, value)
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            wf_per_edge = -(-a.dim * 4 // 128) + 1
-            nnz = sum(t["nnz"] for t in timing if (t["algo"] == 2) and (("gene<-cell" if t["n_dst"] == a.genes else "cell<-gene") == key[1]))
-            achieved_wf = nnz * wf_per_edge / (g["ms"] / 1e3)
-            peak_wf = 148 * sm_mhz * 1e6
-            roofline["onchip"] = {"bound": "lsu_shared_pipe", "unit": "wavefronts/s", "achieved": achieved_wf, "peak": peak_wf,
-                                  "frac": achieved_wf / peak_wf, "wavefronts_per_edge": wf_per_edge, "sm_mhz": sm_mhz}
+        # the resource that actually binds the CSR walk: the LSU / shared-memory data pipe, 1 wavefront (128 B) per
+        # clock per SM; per edge the kernel issues ceil(row bytes / 128) LDS wavefronts for the source row + 1
+        # broadcast LDS.64 for the edge's (column, value).  Reported per direction; a pass that also runs the dense
+        # block (edges_in_dense_block > 0) spends part of its time in the FMA-bound agg_dense kernel, whose edges
+        # are not CSR wavefronts, so its figure understates the CSR kernel (see profiles/ for the split).
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        wf_per_edge = -(-a.dim * 4 // 128) + 1
+        peak_wf = 148 * sm_mhz * 1e6
+        onchip = {}
+        for k2, g2 in groups.items():
+            if k2[0] != "tiled":
+                continue
+            achieved_wf = g2["nnz"] * wf_per_edge / (g2["ms"] / 1e3)
+            onchip[k2[1]] = {"bound": "lsu_shared_pipe", "unit": "wavefronts/s", "achieved": achieved_wf, "peak": peak_wf,
+                             "frac": achieved_wf / peak_wf, "wavefronts_per_edge": wf_per_edge, "sm_mhz": sm_mhz,
+                             "csr_edges_per_launch": g2["nnz"] / g2["n"], "edges_in_dense_block": g2["dense_nnz"] / max(1, g2["dense_nnz"] + g2["nnz"])}
+        if key[1] in onchip:
+            roofline["onchip"] = onchip[key[1]]
+        roofline["onchip_by_direction"] = onchip
 
     # ---- end-to-end through the public API with HOST buffers: `e2e` --------------------------
     e2e = None
