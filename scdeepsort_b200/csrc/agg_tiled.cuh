@@ -402,12 +402,21 @@ agg_tiled_kernel(const TiledParams p) {
                 const int l0 = cur[r] & 31;
                 const unsigned m = __ballot_sync(0xffffffffu, lane >= l0 && ccol[r] < win_end);
                 const int cnt = __popc(m);         // columns ascend: a contiguous run starting at lane l0
-                int k = 0;
-                for (; k + 1 < cnt; k += 2) {          // two edges per iteration: 2x the loads in flight
+                int k = l0;                            // index of the next edge inside the chunk
+                const int2* eb = edge_buf + r * 32 + l0;      // ESM: running pointer into the row's edge mirror
+                for (int pairs = cnt >> 1; pairs > 0; --pairs) {      // two edges per iteration: 2x the loads in flight
                     int c0, c1;
                     float x0, x1;
-                    edge(r, l0 + k, c0, x0);
-                    edge(r, l0 + k + 1, c1, x1);
+                    if (ESM) {
+                        const int2 e0 = eb[0], e1 = eb[1];
+                        eb += 2;
+                        c0 = e0.x; x0 = __int_as_float(e0.y);
+                        c1 = e1.x; x1 = __int_as_float(e1.y);
+                    } else {
+                        edge(r, k, c0, x0);
+                        edge(r, k + 1, c1, x1);
+                        k += 2;
+                    }
                     const float* s0 = stage + (size_t)c0 * pitch;
                     const float* s1 = stage + (size_t)c1 * pitch;
                     float4 a4[S::N4], b4[S::N4];
@@ -432,10 +441,15 @@ agg_tiled_kernel(const TiledParams p) {
                     }
                     if (S::TAIL1) acc[r].v1 = fmaf(x1, b1, fmaf(x0, a1, acc[r].v1));
                 }
-                if (k < cnt) {                           // odd edge left over
+                if (cnt & 1) {                           // odd edge left over
                     int c0;
                     float x0;
-                    edge(r, l0 + k, c0, x0);
+                    if (ESM) {
+                        const int2 e0 = eb[0];
+                        c0 = e0.x; x0 = __int_as_float(e0.y);
+                    } else {
+                        edge(r, k, c0, x0);
+                    }
                     const float* s0 = stage + (size_t)c0 * pitch;
                     float4 a4[S::N4];
                     float a1 = 0.f;
