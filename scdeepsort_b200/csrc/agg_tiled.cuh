@@ -382,10 +382,10 @@ agg_tiled_kernel(const TiledParams p) {
     constexpr bool kTailAllLanes = DIM > 0 && S::TAIL1 && (((DIM + 31) & ~31) - S::J4 * 128 >= 32);
     int s = 0;
     uint32_t ph = 0;
-    int win_end = w_begin * p.win_rows;
-    const float* stage = stages + lane * 4 - (size_t)win_end * pitch;
+    const int win_rows = p.win_rows;
+    int win_end = (w_begin + 1) * win_rows;          // advanced at the END of an iteration: ready before the next wait
+    const float* stage = stages + lane * 4 - (size_t)w_begin * win_rows * pitch;
     for (int w = w_begin; w < w_end; ++w) {
-        win_end += p.win_rows;
         mbar_wait_a(full_a0 + 8u * s, ph);
         if (DIAG == 2) {
             __syncwarp();
@@ -393,6 +393,7 @@ agg_tiled_kernel(const TiledParams p) {
                 mbar_arrive_a(empty_a0 + 8u * s);
                 if (CL > 1) mbar_arrive_remote(&empty_bar[s], cta_rank ^ 1);
             }
+            win_end += win_rows;
             if (++s == kTiledStages) { s = 0; ph ^= 1; stage -= (size_t)kTiledStages * stage_floats; }
             continue;
         }
@@ -477,6 +478,7 @@ agg_tiled_kernel(const TiledParams p) {
             mbar_arrive_a(empty_a0 + 8u * s);
             if (CL > 1) mbar_arrive_remote(&empty_bar[s], cta_rank ^ 1);
         }
+        win_end += win_rows;
         if (++s == kTiledStages) { s = 0; ph ^= 1; stage -= (size_t)kTiledStages * stage_floats; }
     }
 
