@@ -10,7 +10,7 @@
 //
 //   dout[t, :] = SUM_k xd[k, t] * hs[src(k), :]            t < t_total destinations, k < K sources
 //
-// Same CTA shape as the tiled kernel — NW consumer warps x TM destination rows with register-resident
+// Same CTA organisation as the tiled kernel — NW consumer warps x TM destination rows with register-resident
 // accumulators, one producer warp streaming source rows through a shared-memory ring with bulk-async
 // copies — but there is no edge list: for every source row of the window a warp reads the row once
 // (13 wavefronts for 400 floats) and its TM weights with broadcast loads, then issues TM x 13 FMAs.
@@ -28,7 +28,7 @@
 
 namespace wsage {
 
-constexpr int kDenseNW = 12;                       // consumer warps
+constexpr int kDenseNW = 14;                       // consumer warps (+ producer = 15 warps at <= 128 registers); T must be a multiple of 4
 constexpr int kDenseTM = 6;                        // destination rows per warp
 constexpr int kDenseT = kDenseNW * kDenseTM;       // destinations per tile (the blocking of xd)
 constexpr int kDenseStages = 3;                    // default ring depth (WSAGE_DENSE_STAGES = 2 | 3 | 4 for tuning)

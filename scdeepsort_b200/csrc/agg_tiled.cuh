@@ -528,15 +528,22 @@ tiled_reduce_kernel(const TiledParams p) {
 // Kernel shape: consumer warps per CTA, destination rows per warp, depth of the window ring.
 // WSAGE_TILED_VARIANT (env, tuning only) selects among the compiled shapes for dim == 400.
 struct TiledVariant { int nw, r, stages; bool esm; };
-// [0] = default (best of the round-1 sweeps, profiles/r01_summary.md)
-constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}, {12, 4, 2, true}};
+inline int tiled_diag_env() { const char* e = getenv("WSAGE_TILED_DIAG"); const int i = e ? atoi(e) : 0; return (i == 1 || i == 2) ? i : 0; }
+inline int tiled_cluster_env() { const char* e = getenv("WSAGE_TILED_CLUSTER"); return (e && atoi(e) == 2) ? 2 : 1; }
+// [0] = shape of every width but 400 and of the diagnostic / cluster variants; [kTiledDefault400] = default for
+// dim == 400: 15 consumer warps + producer = 16 warps at 128 registers fill the register file exactly, 60 rows
+// per tile instead of 48 (20 % less window-fill traffic, 25 % more warps to hide shared-memory latency):
+// c4 cell<-gene 94.7 -> 87.1 ms, gene<-cell 115.2 -> 106.5 ms (profiles/r01_summary.md)
+constexpr int kTiledDefault400 = 6;
+constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}, {12, 4, 2, true}, {14, 4, 3, true}, {15, 4, 3, true}};
 constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
 
 inline int tiled_variant_index() {
     static const int v = [] {
         const char* e = getenv("WSAGE_TILED_VARIANT");
-        const int i = e ? atoi(e) : 0;
-        return (i >= 0 && i < kNumTiledVariants) ? i : 0;
+        int i = e ? atoi(e) : kTiledDefault400;
+        if (tiled_diag_env() != 0 || tiled_cluster_env() == 2) i = e ? i : 0;     // those variants exist for shape [0] only
+        return (i >= 0 && i < kNumTiledVariants) ? i : kTiledDefault400;
     }();
     return v;
 }
@@ -677,6 +684,8 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledI
                 case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4, true>(a, pl, ini, st);
                 case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, ini, st);
                 case 4: return launch_tiled_shape<ColT, 400, 12, 4, 2, true>(a, pl, ini, st);
+                case 5: return launch_tiled_shape<ColT, 400, 14, 4, 3, true>(a, pl, ini, st);
+                case 6: return launch_tiled_shape<ColT, 400, 15, 4, 3, true>(a, pl, ini, st);
                 default:
                     if (tiled_diag() == 1) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 1>(a, pl, ini, st);
                     if (tiled_diag() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 2>(a, pl, ini, st);
