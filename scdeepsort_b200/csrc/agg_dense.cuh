@@ -187,7 +187,10 @@ inline DensePlan dense_plan(const wsage_spmm_args* a) {
     // few destination tiles (popular genes as destinations): cut the long source range so that the grid
     // covers the chip ~4 times over; many tiles (cells as destinations) need no split
     int splits = 1;
-    if (pl.n_tiles < 2 * kNumSMs) splits = (4 * kNumSMs + pl.n_tiles - 1) / pl.n_tiles;
+    // (rounded DOWN: 14 tiles x 43 splits = 602 CTAs would leave a fifth, nearly empty wave — measured 20.5 ms
+    // against 15.3 ms for 4.0 waves)
+    if (pl.n_tiles < 2 * kNumSMs) splits = (4 * kNumSMs) / pl.n_tiles;
+    if (splits < 1) splits = 1;
     const int max_splits = pl.n_windows / 4 > 0 ? pl.n_windows / 4 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits > kDenseMaxSplits) splits = kDenseMaxSplits;
