@@ -548,7 +548,7 @@ inline int tiled_variant_index() {
     return v;
 }
 inline TiledVariant tiled_variant(const wsage_spmm_args* a) {
-    return kTiledVariants[a->dim == 400 ? tiled_variant_index() : 0];
+    return kTiledVariants[a->dim == 400 ? tiled_variant_index() : kTiledDefault400];     // other widths: the default shape
 }
 
 struct TiledPlan {
@@ -621,12 +621,12 @@ struct TiledInit { const float* init; int slabs; int64_t rows; const int32_t* ma
 // carries no extra branch — a run-time flag in the window loop cost 3.7 % of the step): 1 = the producer copies
 // nothing (edge-walk time only, results meaningless), 2 = the consumers skip the edge walk (window-fill time only).
 inline int tiled_diag() {
-    static const int v = [] { const char* e = getenv("WSAGE_TILED_DIAG"); const int i = e ? atoi(e) : 0; return (i == 1 || i == 2) ? i : 0; }();
+    static const int v = tiled_diag_env();
     return v;
 }
 
-inline int tiled_cluster() {      // WSAGE_TILED_CLUSTER = 1 | 2 (dim 400 default shape only)
-    static const int v = [] { const char* e = getenv("WSAGE_TILED_CLUSTER"); const int i = e ? atoi(e) : kTiledDefaultCluster; return i == 2 ? 2 : 1; }();
+inline int tiled_cluster() {      // WSAGE_TILED_CLUSTER = 1 | 2 (dim 400, shape [0] only)
+    static const int v = kTiledDefaultCluster == 2 ? 2 : tiled_cluster_env();
     return v;
 }
 
@@ -692,9 +692,9 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledI
                     if (tiled_cluster() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 2>(a, pl, ini, st);
                     return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, ini, st);
             }
-        case 200: return launch_tiled_shape<ColT, 200, 12, 4, 3, true>(a, pl, ini, st);
-        case 128: return launch_tiled_shape<ColT, 128, 12, 4, 3, true>(a, pl, ini, st);
-        default:  return launch_tiled_shape<ColT, 0, 12, 4, 3, true>(a, pl, ini, st);
+        case 200: return launch_tiled_shape<ColT, 200, 15, 4, 3, true>(a, pl, ini, st);
+        case 128: return launch_tiled_shape<ColT, 128, 15, 4, 3, true>(a, pl, ini, st);
+        default:  return launch_tiled_shape<ColT, 0, 15, 4, 3, true>(a, pl, ini, st);
     }
 }
 
