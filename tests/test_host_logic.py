@@ -240,3 +240,21 @@ def test_densify_splits_expression_matrix_exactly():
     # nothing popular enough: unchanged
     bg3 = BipartiteGraph.from_expression(x).densify(1.1)
     assert not getattr(bg3, "densified", False) and bg3.gene_csr.dense is None
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """Driver contract: stdout of bench.py is ONE JSON line (library banners go to stderr); the reference arm
+    runs the oracle port on the host cores and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--cells", "4000", "--genes", "500", "--deg", "40", "--dim", "16", "--hidden", "16",
+                           "--cpu-sample-cells", "48"], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

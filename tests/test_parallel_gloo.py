@@ -27,6 +27,18 @@ def _spmm_cpu(csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
               want_raw=False, q=None, want_dot=False, algo=0):
     seg = torch.repeat_interleave(torch.arange(csr.n_dst), csr.rowptr[1:] - csr.rowptr[:-1])
     acc = torch.zeros(csr.n_dst, hs.shape[1]).index_add_(0, seg, hs[_cols(csr)] * csr.x[:, None])
+    d = getattr(csr, "dense", None)
+    if d is not None:          # wsage_spmm_args.dense_*: acc[v] += sum_k xd[slot(v)/T][k][slot(v)%T] * hs[src(k)]
+        tile = sd._lib.load().wsage_dense_tile()
+        n_tiles = (d.t + tile - 1) // tile
+        xd = d.x.view(n_tiles, d.k, tile).permute(1, 0, 2).reshape(d.k, n_tiles * tile)[:, :d.t]      # [source, slot]
+        src = hs if d.src_ids is None else hs[d.src_ids.to(torch.int64)]
+        part = xd.t() @ src                                                                             # [slot, dim]
+        if d.dst_map is None:
+            acc = acc + part
+        else:
+            rows = torch.nonzero(d.dst_map >= 0).flatten()
+            acc[rows] += part[d.dst_map[rows].to(torch.int64)]
     o = acc if dscale is None else acc * dscale[:, None]
     if selfcoef is not None:
         o = o + selfcoef[:, None] * hself
@@ -62,7 +74,7 @@ def _full_reference():
     return bg, feats, logits.detach(), float(loss), {k: p.grad.clone() for k, p in m.named_parameters()}
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, densify=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -72,6 +84,9 @@ def _worker(rank, world, port, q):
         bg = synthetic_bipartite(C, G, DEG, device="cpu", cell_range=(lo, hi))
         parallel.globalize_gene_normalisers(bg)
         feats = synthetic_features(bg, D0)
+        if densify:            # every rank picks ITS OWN popular genes from its local degrees: no coordination needed
+            bg.densify(densify[rank], directions=("gene", "cell") if rank == 0 else ("gene",))
+            assert bg.densified and bg.gene_csr.dense is not None
         m = _model()
         parallel.broadcast_params(m)
         logits = parallel.sharded_forward(m, bg, feats)
@@ -99,12 +114,15 @@ def test_cell_ranges_partition():
         assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
 
 
-def test_two_rank_sharded_step_matches_single_process():
+@pytest.mark.parametrize("densify", [None, (0.15, 0.3)])
+def test_two_rank_sharded_step_matches_single_process(densify):
+    """densify: each rank moves its own (different) popular-gene set into dense blocks — the all-reduced gene sums
+    and the gradients must not change."""
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, densify)) for r in range(world)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
     [p.join(timeout=60) for p in procs]
