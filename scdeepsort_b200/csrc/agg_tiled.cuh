@@ -535,7 +535,7 @@ inline int tiled_cluster_env() { const char* e = getenv("WSAGE_TILED_CLUSTER"); 
 // per tile instead of 48 (20 % less window-fill traffic, 25 % more warps to hide shared-memory latency):
 // c4 cell<-gene 94.7 -> 87.1 ms, gene<-cell 115.2 -> 106.5 ms (profiles/r01_summary.md)
 constexpr int kTiledDefault400 = 6;
-constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}, {12, 4, 2, true}, {14, 4, 3, true}, {15, 4, 3, true}};
+constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}, {12, 4, 2, true}, {14, 4, 3, true}, {15, 4, 3, true}, {15, 4, 4, true}, {15, 4, 2, true}};
 constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
 
 inline int tiled_variant_index() {
@@ -686,6 +686,8 @@ int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledI
                 case 4: return launch_tiled_shape<ColT, 400, 12, 4, 2, true>(a, pl, ini, st);
                 case 5: return launch_tiled_shape<ColT, 400, 14, 4, 3, true>(a, pl, ini, st);
                 case 6: return launch_tiled_shape<ColT, 400, 15, 4, 3, true>(a, pl, ini, st);
+                case 7: return launch_tiled_shape<ColT, 400, 15, 4, 4, true>(a, pl, ini, st);      // not yet measured
+                case 8: return launch_tiled_shape<ColT, 400, 15, 4, 2, true>(a, pl, ini, st);      // not yet measured
                 default:
                     if (tiled_diag() == 1) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 1>(a, pl, ini, st);
                     if (tiled_diag() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 2>(a, pl, ini, st);
