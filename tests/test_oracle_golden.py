@@ -134,3 +134,22 @@ def test_unsure_rule():
     logits = torch.tensor([[5.0, 0, 0, 0], [0.1, 0, 0, 0]])
     assert gnn_oracle.predict_labels(logits, 2.0).tolist() == [0, -1]    # 0.27 < 2/4 → unsure
     assert gnn_oracle.predict_labels(logits, 0.0).tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("n_layers", [1, 2, 3])
+def test_closed_form_spmm_oracle_matches_literal_oracle(n_layers):
+    """oracle/spmm_oracle.py (bench.py's optimised CPU baseline: sparse-CSR products, no message tensor) computes
+    the same logits as the literal edge-materialising restatement of models/gnn.py:47-68."""
+    import scipy.sparse as sp
+    from oracle import spmm_oracle
+    rng = np.random.RandomState(n_layers)
+    c, g, d, h, k = 60, 40, 8, 12, 4
+    x = sp.csr_matrix(np.where(rng.rand(c, g) < 0.2, rng.rand(c, g) + 0.1, 0).astype(np.float32))
+    og = graph_oracle.build_graph(x)
+    og.features = torch.randn(g + c, d, generator=torch.Generator().manual_seed(0))
+    params = gnn_oracle.init_params(d, h, k, n_layers, g, perturb_alpha=True)
+    flow = graph_oracle.full_neighbor_flow(og, torch.arange(g, g + c), n_layers)
+    ref = gnn_oracle.forward(params, flow, g, dtype=torch.float64)
+    out = spmm_oracle.forward({n: v.double() for n, v in params.items()}, spmm_oracle.SpmmGraph(x, torch.float64),
+                              og.features.double(), n_layers)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-6
