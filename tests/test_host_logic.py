@@ -258,3 +258,34 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the ABI-1001 additions run before any CUDA call, so they are testable here."""
+    import ctypes
+    lib = sd._lib.load()
+    assert lib.wsage_version() >= 1001 and lib.wsage_dense_tile() % 4 == 0
+    # accumulation chains of the weight gradient are capped at 1024 rows (64 k-blocks of 16)
+    assert lib.wsage_grad_w_splits(780_000, 400) == -(-(-(-780_000 // 16)) // 64) == 762
+    assert lib.wsage_grad_w_splits(1000, 400) == 1 and lib.wsage_grad_w_splits(0, 400) == 0
+    one = ctypes.c_void_p(16)          # non-null, 16-byte aligned dummy: never dereferenced on these paths
+    rc = lib.wsage_grad_w_tc(one, one, 400, one, one, 400, 1000, 398, 400, one, 1, one, 400, None)
+    assert rc == sd._lib.EINVAL and b"multiples of 4" in lib.wsage_last_error()
+    rc = lib.wsage_grad_w_tc(one, one, 400, one, one, 600, 1000, 400, 600, one, 1, one, 600, None)
+    assert rc == sd._lib.EINVAL and b"512" in lib.wsage_last_error()
+    rc = lib.wsage_grad_w_tc(one, one, 400, one, one, 400, 100_000, 400, 400, one, 3, one, 400, None)
+    assert rc == sd._lib.EINVAL and b"wsage_grad_w_splits" in lib.wsage_last_error()
+    a = sd._lib.SpmmArgs()
+    a.n_dst, a.n_src, a.dim, a.col_bits, a.nnz = 8, 8, 400, 32, 4
+    a.rowptr = a.hs = a.out = one
+    a.ld_hs = a.ld_out = 400
+    a.dense_x, a.dense_k, a.dense_t = one, 0, 8
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"dense_k" in lib.wsage_last_error()
+    a.dense_k, a.dense_t = 5, 8                     # dense_src_ids == NULL needs dense_k == n_src
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"dense_src_ids" in lib.wsage_last_error()
+    a.dense_k, a.algo = 8, 1                        # the gather kernel cannot take a dense block
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"tiled" in lib.wsage_last_error()
+    assert lib.wsage_spmm_algo(ctypes.byref(a)) == 0
+    a.algo = 0
+    assert lib.wsage_spmm_algo(ctypes.byref(a)) == 2                  # a dense block always takes the tiled kernel
+    assert lib.wsage_spmm_workspace_bytes(ctypes.byref(a)) >= 8 * 400 * 4
