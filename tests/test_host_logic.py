@@ -289,3 +289,40 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     a.algo = 0
     assert lib.wsage_spmm_algo(ctypes.byref(a)) == 2                  # a dense block always takes the tiled kernel
     assert lib.wsage_spmm_workspace_bytes(ctypes.byref(a)) >= 8 * 400 * 4
+
+
+def test_densify_with_test_cells_splits_all_three_csrs():
+    """Inference graphs carry test cells (gene->cell only, utils/preprocess.py:185-187): gene_csr covers the support
+    cells, cell_csr_t is the transpose of the full cell_csr; densify must split both gene-destination CSRs."""
+    import scipy.sparse as sp
+    from scdeepsort_b200.graph import BipartiteGraph
+    rng = np.random.RandomState(5)
+    cs, ct, g = 120, 30, 90
+    pop = np.minimum(1, 2.5 * np.arange(1, g + 1) ** -0.8)[rng.permutation(g)]
+    xs = sp.csr_matrix(np.where(rng.rand(cs, g) < pop[None, :], rng.rand(cs, g) + 0.1, 0).astype(np.float32))
+    xt = sp.csr_matrix(np.where(rng.rand(ct, g) < pop[None, :], rng.rand(ct, g) + 0.1, 0).astype(np.float32))
+    bg = BipartiteGraph.from_expression(xs, xt).densify(0.25)
+    assert bg.densified and bg.cell_csr.dense is None
+    tile = sd._lib.load().wsage_dense_tile()
+
+    def dense_rows(csr):            # [n_dst, n_src] contribution of the dense block
+        d = csr.dense
+        nt = (d.t + tile - 1) // tile
+        xd = d.x.view(nt, d.k, tile).permute(1, 0, 2).reshape(d.k, nt * tile)[:, :d.t].numpy()
+        out = np.zeros((csr.n_dst, csr.n_src), dtype=np.float32)
+        slots = d.dst_map.numpy()
+        rows = np.nonzero(slots >= 0)[0]
+        out[rows, :] = xd[:, slots[rows]].T
+        return out
+
+    def csr_rows(csr):
+        col = csr.col.to(torch.int64)
+        if csr.col_bits == 16:
+            col = col & 0xFFFF
+        return sp.csr_matrix((csr.x.numpy(), col.numpy(), csr.rowptr.numpy()), shape=(csr.n_dst, csr.n_src)).toarray()
+
+    full = sp.vstack([xs, xt]).toarray()
+    assert np.array_equal(csr_rows(bg.gene_csr) + dense_rows(bg.gene_csr), xs.toarray().T)
+    assert np.array_equal(csr_rows(bg.cell_csr_t) + dense_rows(bg.cell_csr_t), full.T)
+    assert np.array_equal(csr_rows(bg.cell_csr), full)
+    assert bg.transpose_of_cell_csr() is bg.cell_csr_t
