@@ -43,9 +43,12 @@ def parse():
     ap.add_argument("--hidden", type=int, default=400)
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--algo", type=int, default=0, help="wsage_spmm algo (0 auto, 1 gather, 2 tiled)")
-    ap.add_argument("--dense-threshold", type=float, default=0.3,
-                    help="genes expressed in at least this share of the cells leave the gene-destination CSR and run on the "
-                         "dense-block kernel (BipartiteGraph.densify); 0 = CSR only")
+    ap.add_argument("--dense-threshold", type=float, default=0.0,
+                    help="genes expressed in at least this share of the cells leave the CSRs and run on the tensor-core "
+                         "dense-block kernel (BipartiteGraph.densify); 0 = every gene, negative = CSR only")
+    ap.add_argument("--dense-fmt", default="f16x2", choices=["f16x2", "bf16"],
+                    help="f16x2 = fp16 hi+lo planes, three products (fp32-grade); bf16 = one product (BASELINE configs[2])")
+    ap.add_argument("--dropout", type=float, default=0.0)
     ap.add_argument("--cpu-sample-cells", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -186,7 +189,23 @@ def algorithmic_bytes(t):
     s = 4
     idx = 2 if t["col_bits"] == 16 else 4
     streams = t["n_out"] + (1 if t["self"] else 0) + (1 if t["dot"] else 0)
-    return (t["nnz"] + t.get("dense_nnz", 0)) * (idx + 4) + (t["n_dst"] + 1) * 8 + t["n_src"] * t["dim"] * s + streams * t["n_dst"] * t["dim"] * s
+    return t["nnz"] * (idx + 4) + (t["n_dst"] + 1) * 8 + t["n_src"] * t["dim"] * s + streams * t["n_dst"] * t["dim"] * s
+
+
+def dense16_work(t):
+    """What one wsage_dense16 launch does.  flops: the MMAs it issues (3 products for fp16 hi+lo, zeros included);
+    useful_flops: 2·D per expression entry the block stands for; plane_bytes: the X planes it streams from HBM once
+    (hi + lo, 2 bytes each per (cell, slot)); algorithmic_bytes: SURVEY §8(d) for the same entries as a CSR
+    (6 B per entry: uint16 index + fp32 value) + the source and destination rows once."""
+    terms = 3 if t["fmt"] == 0 else 1
+    cells_pad = -(-t["cells"] // 128) * 128
+    n_pad = -(-t["dim"] // 16) * 16
+    k_side0 = -(-t["gene_slots"] // 32) * 32
+    pairs = cells_pad * (k_side0 if t["side"] == 0 else t["slots_pad"])
+    n_src, n_dst = (t["gene_slots"], t["cells"]) if t["side"] == 0 else (t["cells"], t["gene_slots"])
+    return dict(flops=terms * 2 * pairs * n_pad, useful_flops=2 * t["dense_nnz"] * t["dim"],
+                plane_bytes=(2 if terms == 3 else 1) * 2 * t["cells"] * t["slots_pad"],
+                algorithmic_bytes=t["dense_nnz"] * 6 + (n_src + n_dst) * t["dim"] * 4)
 
 
 def run_ours(a):
@@ -213,13 +232,13 @@ def run_ours(a):
     parallel.globalize_gene_normalisers(graph)
     feats = synthetic_features(graph, a.dim, seed=SEED)
     labels = torch.randint(0, NUM_CLASSES, (a.cells,), generator=torch.Generator().manual_seed(SEED))[lo:hi].to(dev)
-    if a.dense_threshold > 0:
-        graph.densify(a.dense_threshold)
+    if a.dense_threshold >= 0:
+        graph.densify(a.dense_threshold, fmt=a.dense_fmt)
     torch.cuda.synchronize()
     build_s = time.time() - t0
 
     trainer = FullGraphTrainer(graph, NUM_CLASSES, dense_dim=a.dim, hidden_dim=a.hidden, n_layers=a.layers,
-                               dropout=0.0, seed=SEED, sharded=world > 1, spmm_algo=a.algo)
+                               dropout=a.dropout, seed=SEED, sharded=world > 1, spmm_algo=a.algo)
     parallel.broadcast_params(trainer.model)
 
     def barrier():
@@ -259,59 +278,64 @@ def run_ours(a):
     final_loss = float(loss)
 
     # ---- roofline of the dominant aggregation kernel (per-launch CUDA events, timed region) ----
-    groups = {}
-    for t in timing:
-        key = ("tiled" if t["algo"] == 2 else "gather", "gene<-cell" if t["n_dst"] == a.genes else "cell<-gene")
-        g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0, gather_bytes=0))
-        g["ms"] += t["events"][0].elapsed_time(t["events"][1])
-        g["n"] += 1
-        g["bytes"] += algorithmic_bytes(t)
-        g["gather_bytes"] += (t["nnz"] + t.get("dense_nnz", 0)) * t["dim"] * 4
-        g["dense_nnz"] = g.get("dense_nnz", 0) + t.get("dense_nnz", 0)
-        g["nnz"] = g.get("nnz", 0) + t["nnz"]
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
         peaks = json.loads(pk.read_text())
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    # a kernel timed inside a long step: the sustained tensor figure
+    tc_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0))
+    groups = {}
+    for t in timing:
+        ms = t["events"][0].elapsed_time(t["events"][1])
+        if t["kind"] == "dense16":
+            key = ("dense16", "cell<-gene" if t["side"] == 0 else "gene<-cell")
+            w = dense16_work(t)
+            g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0, flops=0, useful_flops=0, plane_bytes=0, nnz=0))
+            g["flops"] += w["flops"]; g["useful_flops"] += w["useful_flops"]; g["plane_bytes"] += w["plane_bytes"]
+            g["bytes"] += w["algorithmic_bytes"]; g["nnz"] += t["dense_nnz"]
+        else:
+            key = ({2: "tiled", 1: "gather", 0: "reduce"}[t["algo"]], "gene<-cell" if t["n_dst"] == a.genes else "cell<-gene")
+            g = groups.setdefault(key, dict(ms=0.0, n=0, bytes=0, nnz=0))
+            g["bytes"] += algorithmic_bytes(t); g["nnz"] += t["nnz"]
+        g["ms"] += ms
+        g["n"] += 1
     roofline, kernels = None, {}
     if groups:
         for key, g in groups.items():
-            kernels[f"{key[0]}:{key[1]}"] = {
-                "launches": g["n"], "ms_per_launch": g["ms"] / g["n"], "share_of_step": g["ms"] / a.steps / ms_step,
-                "algorithmic_gbs": g["bytes"] / g["ms"] / 1e6, "gather_side_tbs": g["gather_bytes"] / g["ms"] / 1e9,
-                "edges_in_dense_block": g["dense_nnz"] / max(1, g["dense_nnz"] + g["nnz"])}
+            k = {"launches": g["n"], "ms_per_launch": g["ms"] / g["n"], "share_of_step": g["ms"] / a.steps / ms_step,
+                 "algorithmic_gbs": g["bytes"] / g["ms"] / 1e6, "entries_per_launch": g["nnz"] / g["n"]}
+            if key[0] == "dense16":
+                k.update(mma_tflops=g["flops"] / g["ms"] / 1e9, useful_tflops=g["useful_flops"] / g["ms"] / 1e9,
+                         hbm_plane_stream_gbs=g["plane_bytes"] / g["ms"] / 1e6)
+            kernels[f"{key[0]}:{key[1]}"] = k
         key, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
-        achieved = g["bytes"] / g["ms"] / 1e6
         traffic = None          # ncu dram bytes per launch, recorded under profiles/ for the c4 shape
-        tj = ROOT / "profiles" / "r01_traffic.json"
+        tj = ROOT / "profiles" / "r02_traffic.json"
         if tj.exists() and (a.cells, a.genes, int(a.deg), a.dim, world) == (760_000, 20_000, 2000, 400, 1):
-            traffic = json.loads(tj.read_text())["c4"].get(f"{key[0]}:{key[1]}")
-        roofline = {"kernel": f"agg_{key[0]} ({key[1]})", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                    "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "ms_per_launch": g["ms"] / g["n"],
-                    "gather_side_tbs": g["gather_bytes"] / g["ms"] / 1e9,
-                    "note": "algorithmic bytes count distinct rows once (SURVEY 8d); the E*D gather is served "
-                            "on-chip (L2/L1/smem), reported as gather_side_tbs and bounded by onchip"}
-        # the resource that actually binds the CSR walk: the LSU / shared-memory data pipe, 1 wavefront (128 B) per
-        # clock per SM; per edge the kernel issues ceil(row bytes / 128) LDS wavefronts for the source row + 1
-        # broadcast LDS.64 for the edge's (column, value).  Reported per direction; a pass that also runs the dense
-        # block (edges_in_dense_block > 0) spends part of its time in the FMA-bound agg_dense kernel, whose edges
-        # are not CSR wavefronts, so its figure understates the CSR kernel (see profiles/ for the split).
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        wf_per_edge = -(-a.dim * 4 // 128) + 1
-        peak_wf = 148 * sm_mhz * 1e6
-        onchip = {}
-        for k2, g2 in groups.items():
-            if k2[0] != "tiled":
-                continue
-            achieved_wf = g2["nnz"] * wf_per_edge / (g2["ms"] / 1e3)
-            onchip[k2[1]] = {"bound": "lsu_shared_pipe", "unit": "wavefronts/s", "achieved": achieved_wf, "peak": peak_wf,
-                             "frac": achieved_wf / peak_wf, "wavefronts_per_edge": wf_per_edge, "sm_mhz": sm_mhz,
-                             "csr_edges_per_launch": g2["nnz"] / g2["n"], "edges_in_dense_block": g2["dense_nnz"] / max(1, g2["dense_nnz"] + g2["nnz"])}
-        if key[1] in onchip:
-            roofline["onchip"] = onchip[key[1]]
-        roofline["onchip_by_direction"] = onchip
+            traffic = json.loads(tj.read_text()).get("c4", {}).get(f"{key[0]}:{key[1]}")
+        if key[0] == "dense16":
+            achieved = g["flops"] / g["ms"] / 1e9
+            roofline = {"kernel": f"dense16_kernel ({key[1]})", "bound": "tensor", "achieved": achieved, "peak": tc_peak,
+                        "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kind::f16 MMAs run at the bf16 rate)"
+                        if peaks else "fallback", "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": traffic,
+                        "mma_flops_per_launch": g["flops"] / g["n"], "ms_per_launch": g["ms"] / g["n"],
+                        "useful_tflops": g["useful_flops"] / g["ms"] / 1e9,
+                        "hbm": {"algorithmic_gbs": g["bytes"] / g["ms"] / 1e6, "plane_stream_gbs": g["plane_bytes"] / g["ms"] / 1e6,
+                                "peak_gbs": hbm_peak, "algorithmic_frac": g["bytes"] / g["ms"] / 1e6 / hbm_peak,
+                                "plane_stream_frac": g["plane_bytes"] / g["ms"] / 1e6 / hbm_peak,
+                                "algorithmic_bytes_per_launch": g["bytes"] / g["n"]},
+                        "note": "achieved = MMA flops the kernel issues (fp16 hi*hi + lo*hi + hi*lo over the zero-filled block) / its "
+                                "CUDA-event time; useful_tflops = 2*D per expression entry; hbm.algorithmic = SURVEY 8d bytes of the "
+                                "same entries as a CSR, hbm.plane_stream = the 16-bit planes the kernel actually streams"}
+        else:
+            achieved = g["bytes"] / g["ms"] / 1e6
+            roofline = {"kernel": f"agg_{key[0]} ({key[1]})", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                        "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                        "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "ms_per_launch": g["ms"] / g["n"],
+                        "gather_side_tbs": g["nnz"] * a.dim * 4 / g["ms"] / 1e9,
+                        "note": "algorithmic bytes count distinct rows once (SURVEY 8d); the E*D gather is served "
+                                "on-chip (L2/L1/smem), reported as gather_side_tbs"}
 
     # ---- end-to-end through the public API with HOST buffers: `e2e` --------------------------
     e2e = None
@@ -347,9 +371,10 @@ def run_ours(a):
         print(json.dumps({
             "metric": "cells/sec (forward+backward)", "value": a.cells / (ms_step / 1e3), "unit": "cells/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.dense_fmt == "f16x2" else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "cells": a.cells, "genes": a.genes, "nnz_per_rank": graph.nnz,
-                       "dense_threshold": a.dense_threshold, "dense_genes": int(len(getattr(graph, "dense_genes", []))),
+                       "dense_threshold": a.dense_threshold, "dense_fmt": a.dense_fmt, "dense_genes": int(len(getattr(graph, "dense_genes", []))),
+                       "csr_entries_left": graph.cell_csr.nnz, "dropout": a.dropout,
                        "parallelism": f"cell-sharded x{world}" if world > 1 else "single GPU",
                        "l2_policy": "inputs_exceed_l2 (graph + activations >> 126 MB; no explicit flush)",
                        "graph_build_s": build_s, "final_loss_per_cell": final_loss / (hi - lo)},

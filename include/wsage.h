@@ -120,27 +120,78 @@ typedef struct wsage_spmm_args {
     int32_t        algo;
     void*          workspace;
     size_t         workspace_bytes;
-    /* Optional dense block (ABI >= 1001): entries of the popular genes, removed from the CSR and stored
-     * zero-filled as xd[tile][k][T] (T = wsage_dense_tile(), tile = destination slot / T, k = source
-     * index), handled by an FMA-bound kernel whose sums seed the CSR kernel's accumulators:
-     *   acc[v,:] += SUM_k xd[slot(v)/T][k][slot(v)%T] * hs[src(k),:]
-     * src(k) = dense_src_ids[k] (NULL: k, then dense_k == n_src).  slot(v) = dense_dst_map[v]
-     * (< 0: row not in the block.  NULL: v, then dense_t == n_dst).  Needs the tiled kernel's
-     * preconditions (dim % 4 == 0, dim <= 512, contiguous 16-byte aligned hs). */
-    const float*   dense_x;        /* NULL = no dense block                                  */
-    int64_t        dense_k;        /* sources of the block                                   */
-    int64_t        dense_t;        /* destination slots of the block                         */
-    const int32_t* dense_src_ids;  /* [dense_k] or NULL                                      */
-    const int32_t* dense_dst_map;  /* [n_dst]  or NULL                                       */
+    /* Optional seed of the accumulators (ABI >= 2000): partial sums of entries that are not in the CSR — the
+     * popular genes' dense block computed by wsage_dense16 — added in slab order before the CSR walk:
+     *   acc[v,:] = SUM_k init[k][slot(v)][:] + SUM_{e in row v} ...     slot(v) = init_map[v] (negative: no seed for v. NULL: v)
+     * With init the CSR may be empty (nnz == 0): the call then only sums the slabs and applies the epilogue.
+     * Needs dim % 4 == 0, dim <= 512 and 16-byte aligned rows. */
+    const float*   init;           /* [init_slabs][init_rows][dim] or NULL                   */
+    int32_t        init_slabs;
+    int64_t        init_rows;      /* rows per slab                                          */
+    const int32_t* init_map;       /* [n_dst] or NULL                                        */
 } wsage_spmm_args;
-
-/* Destination slots per tile of the dense block's blocked layout. */
-int wsage_dense_tile(void);
 
 size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a);
 /* The kernel wsage_spmm would run for these arguments: 1 (gather) or 2 (tiled); 0 on bad args. */
 int wsage_spmm_algo(const wsage_spmm_args* a);
 int wsage_spmm(const wsage_spmm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense block of the popular genes on the tensor cores (tcgen05 / TMEM / TMA).
+ *
+ * Same reference lines as wsage_spmm (message_func + fn.mean, /root/reference/models/gnn.py:47-56,65), for the
+ * entries X_dense of the expression matrix that the graph builder moved out of the CSRs (genes expressed in more
+ * than a few percent of the cells).  X_dense is stored ONCE, zero-filled, as 16-bit tiles
+ *   plane[cell / 128][slot / 32][cell % 128][slot % 32]      (slot = dense index of the gene, padded to 128)
+ * and serves both directions:
+ *   side 0  out[c,:]  = dscale[c] * SUM_s X[c,s] * H[gene(s),:] + selfcoef[c] * hself[c,:]       c < n_dst
+ *   side 1  out[k][s,:] = SUM_{c in split k} X[c,s] * H[c,:]       partial sums, [n_splits][slots_pad][dim]
+ * (side 1 feeds wsage_spmm's `init`).  fmt WSAGE_D16_F16X2: fp32-grade — X and H are given as fp16 hi + lo
+ * planes of value * 2^k (x_scale for X, chosen at build time; H by wsage_split16 from its amax) and
+ * hi*hi + lo*hi + hi*lo is accumulated in fp32, chains cut every chunk_rows rows.  fmt WSAGE_D16_BF16: bf16
+ * planes, one product (lo pointers ignored).
+ *
+ * wsage_amax:    *amax = max(*amax, max |x[r,c] * rowscale[r]|) over rows r (or row_ids[r]) — caller zero-initialises.
+ * wsage_split16: hi/lo = 16-bit split of x[r,c] * rowscale[r] * 2^k(amax); transpose == 0: planes [rows][ld_out];
+ *                transpose != 0: planes [cols][ld_out] with the (gathered) rows as columns.  ld_out % 8 == 0.
+ * ------------------------------------------------------------------------------------- */
+#define WSAGE_D16_F16X2 0
+#define WSAGE_D16_BF16  1
+
+int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
+               int64_t rows, int32_t cols, float* amax, void* stream);
+int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
+                  int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t transpose,
+                  void* hi, void* lo, int64_t ld_out, void* stream);
+
+typedef struct wsage_dense16_args {
+    const void*    x_hi;         /* 16-bit planes of X_dense (layout above)                              */
+    const void*    x_lo;         /* NULL for WSAGE_D16_BF16                                              */
+    int32_t        fmt;
+    int64_t        cells;        /* cells the planes cover (storage: ceil(cells / 128) tiles)            */
+    int32_t        gene_slots;   /* dense genes (storage: wsage_dense16_slots_pad(gene_slots) slots)     */
+    float          x_scale;      /* stored value = x * x_scale (a power of two)                          */
+    int32_t        side;
+    const void*    h_hi;         /* side 0: [dim][ld_h] (H^T over the dense genes); side 1: [n_src_cells][ld_h] */
+    const void*    h_lo;
+    int64_t        ld_h;         /* elements, multiple of 8                                              */
+    const float*   h_amax;       /* device scalar wsage_split16 scaled by (NULL: unscaled)               */
+    int32_t        dim;
+    int64_t        n_dst;        /* side 0: destination cells (<= cells)                                 */
+    int64_t        n_src_cells;  /* side 1: cells that send (<= cells)                                   */
+    const float*   dscale;       /* side 0, optional                                                     */
+    const float*   selfcoef;     /* side 0, optional (then hself)                                        */
+    const float*   hself;
+    int64_t        ld_hself;
+    float*         out;          /* side 0: [n_dst, dim] (row pitch below), side 1: contiguous slabs   */
+    int64_t        ld_out;
+    int32_t        chunk_rows;   /* accumulation chain length, 0 = default (2048)                        */
+} wsage_dense16_args;
+
+int wsage_dense16_slots_pad(int32_t gene_slots);
+/* side 1: number of partial slabs the call writes (0 on bad arguments). */
+int wsage_dense16_splits(const wsage_dense16_args* a);
+int wsage_dense16(const wsage_dense16_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Post-aggregate dense layer on the tensor cores (tcgen05 / TMEM / TMA).

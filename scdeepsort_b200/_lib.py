@@ -15,9 +15,11 @@ LIB_PATH = CSRC / "libwsage.so"
 OK, EINVAL, EUNSUPPORTED, ECUDA = 0, 1, 2, 3
 COL_I32, COL_U16 = 32, 16
 ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
+D16_F16X2, D16_BF16 = 0, 1
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
-           "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_dense_tile",
+           "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_amax", "wsage_split16",
+           "wsage_dense16_slots_pad", "wsage_dense16_splits", "wsage_dense16",
            "wsage_split_tf32", "wsage_linear_tc", "wsage_grad_w_splits", "wsage_grad_w_tc", "wsage_sample_neighbors",
            "wsage_softmax_ce", "wsage_adam_step")
 
@@ -31,8 +33,18 @@ class SpmmArgs(Structure):
         ("out", c_void_p), ("ld_out", c_int64), ("raw", c_void_p), ("ld_raw", c_int64),
         ("q", c_void_p), ("ld_q", c_int64), ("dot", c_void_p), ("row_perm", c_void_p),
         ("algo", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
-        ("dense_x", c_void_p), ("dense_k", c_int64), ("dense_t", c_int64),
-        ("dense_src_ids", c_void_p), ("dense_dst_map", c_void_p),
+        ("init", c_void_p), ("init_slabs", c_int32), ("init_rows", c_int64), ("init_map", c_void_p),
+    ]
+
+
+class Dense16Args(Structure):
+    """Mirror of ``wsage_dense16_args`` (include/wsage.h)."""
+    _fields_ = [
+        ("x_hi", c_void_p), ("x_lo", c_void_p), ("fmt", c_int32), ("cells", c_int64), ("gene_slots", c_int32),
+        ("x_scale", c_float), ("side", c_int32), ("h_hi", c_void_p), ("h_lo", c_void_p), ("ld_h", c_int64),
+        ("h_amax", c_void_p), ("dim", c_int32), ("n_dst", c_int64), ("n_src_cells", c_int64),
+        ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
+        ("out", c_void_p), ("ld_out", c_int64), ("chunk_rows", c_int32),
     ]
 
 
@@ -76,7 +88,17 @@ def load():
     lib.wsage_spmm_algo.argtypes = [POINTER(SpmmArgs)]
     lib.wsage_spmm.restype = c_int32
     lib.wsage_spmm.argtypes = [POINTER(SpmmArgs), c_void_p]
-    lib.wsage_dense_tile.restype = c_int32
+    lib.wsage_amax.restype = c_int32
+    lib.wsage_amax.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.wsage_split16.restype = c_int32
+    lib.wsage_split16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32,
+                                  c_void_p, c_void_p, c_int64, c_void_p]
+    lib.wsage_dense16_slots_pad.restype = c_int32
+    lib.wsage_dense16_slots_pad.argtypes = [c_int32]
+    lib.wsage_dense16_splits.restype = c_int32
+    lib.wsage_dense16_splits.argtypes = [POINTER(Dense16Args)]
+    lib.wsage_dense16.restype = c_int32
+    lib.wsage_dense16.argtypes = [POINTER(Dense16Args), c_void_p]
     lib.wsage_split_tf32.restype = c_int32
     lib.wsage_split_tf32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                      c_void_p, c_int64, c_int64, c_int32, c_void_p]

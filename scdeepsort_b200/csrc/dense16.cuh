@@ -1,0 +1,530 @@
+// The popular genes' share of the bipartite aggregation on the 5th-generation tensor cores (sm_100a).
+//
+// For a gene expressed in more than a few percent of the cells, walking its edges one by one (agg_tiled.cuh:
+// 14 shared-memory wavefronts per edge) costs more than multiplying through its zeros on tcgen05.  The graph
+// builder therefore splits  X = X_sparse + X_dense : the dense part is stored zero-filled as 16-bit tiles and
+//
+//   side 0 (destinations = cells):  acc[c,:] = SUM_s  Xd[c,s] * H[gene(s),:]     A = Xd (K-major),  B = H^T (K-major)
+//   side 1 (destinations = genes):  acc[s,:] = SUM_c  Xd[c,s] * H[c,:]           A = Xd (MN-major), B = H   (MN-major)
+//
+// run as GEMMs from ONE copy of Xd.  This replaces, for those entries, exactly what agg_tiled_kernel / the
+// reference's message_func + fn.mean do (/root/reference/models/gnn.py:47-56,65).
+//
+// fp32 parity.  Operands are split into fp16 hi + fp16 lo after a power-of-two scaling into fp16's range
+// (x: static, at build time; H: per pass, from its amax), and hi*hi + lo*hi + hi*lo is accumulated in fp32 TMEM:
+// products of two 11-bit significands are exact in fp32, the dropped lo*lo term is 2^-22 relative — the same
+// grade as the tf32x3 scheme of dense_tc.cuh at twice the MMA rate and half the bytes.  The tensor core adds into
+// its accumulator with truncation, so a chain is cut every `chunk_kb` k-blocks (2048 rows): the accumulator is
+// drained, scaled and ADDED to the output tile in global memory by a TMA reduce (cp.reduce.async.bulk.tensor .add,
+// fp32 round-to-nearest in L2; one pending add per address, so the result is order-independent and bitwise
+// reproducible).  fmt = bf16: one product, no scaling (BASELINE configs[2]).
+//
+// Storage of Xd (hi and lo planes alike): [cell tile of 128][gene block of 32][128 cells][32 slots] 16-bit, i.e.
+// rows of 64 bytes.  Seen as a 2-D tensor of 64-byte rows, a TMA box {32, 128} is one contiguous 8 KB K-major
+// A tile for side 0 and a box {32, 32} is a contiguous 2 KB piece of the MN-major A tile for side 1: with the
+// 64-byte swizzle both are canonical UMMA layouts (K-major SW64: 8-row groups 512 B apart; MN-major SW64: 32
+// contiguous MN elements, 8-row K atoms 512 B apart, MN blocks one box apart), so HBM is streamed in whole
+// 8-32 KB pieces in both directions.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5
+// drain (tcgen05.ld -> scale -> swizzled shared-memory staging -> TMA store / reduce-add).  Persistent over
+// (destination tile, k-range) work items, static round-robin.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "dense_tc.cuh"
+
+namespace wsage {
+
+constexpr int kD16TileM = 128;                 // destinations per tile = MMA M = cells per storage tile
+constexpr int kD16BlockK = 32;                 // 16-bit elements per 64-byte row = k-block
+constexpr int kD16UmmaK = 16;                  // K of one tcgen05.mma.kind::f16
+constexpr int kD16ABytes = kD16TileM * 64;     // 8 KB: one A tile (hi or lo)
+constexpr int kD16BoxMN = 32 * 64;             // 2 KB: one {32, 32} box of the MN-major operands
+constexpr int kD16Threads = 192;
+constexpr int kD16OutCols = 16;                // fp32 columns per TMA store box (64 bytes)
+constexpr int kD16StagingBytes = 4 * 2 * 32 * 64;      // 4 drain warps x 2 buffers x [32 rows][64 B]
+constexpr int kD16DefaultChunkRows = 2048;
+constexpr int kD16MaxStages = 6;
+constexpr int kD16SmemBudget = 227 * 1024;
+
+// ------------------------------------------------------------------------------------------------
+// dynamic power-of-two scale of the per-pass operand: amax * scale in [2^13, 2^14)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int d16_scale_exp(float amax) {
+    if (!(amax > 0.f) || amax > 3.0e38f) return 0;
+    int e;
+    frexpf(amax, &e);                           // amax = m * 2^e, m in [0.5, 1)
+    int k = 14 - e;
+    return k > 100 ? 100 : (k < -100 ? -100 : k);
+}
+
+__global__ void __launch_bounds__(256)
+amax_kernel(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__ row_ids, const float* __restrict__ rowscale,
+            int64_t rows, int cols, unsigned* __restrict__ out) {
+    const int64_t n4 = cols / 4;
+    const int64_t total = rows * n4;
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        const int64_t src = row_ids ? (int64_t)__ldg(row_ids + r) : r;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + src * ld + c));
+        const float s = rowscale ? fabsf(__ldg(rowscale + src)) : 1.f;
+        m = fmaxf(m, s * fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float wm[8];
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+        atomicMax(out, __float_as_uint(m));     // non-negative floats order like their bit patterns
+    }
+}
+
+__device__ __forceinline__ void d16_split(float v, int fmt, unsigned short& hi, unsigned short& lo) {
+    if (fmt == 0) {
+        const __half h = __float2half_rn(v);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    } else {
+        hi = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        lo = 0;
+    }
+}
+
+// rows stay rows: hi/lo[r, c] = split(x[r, c] * rowscale[r] * 2^k)           (the side-1 operand H[cells, dim])
+__global__ void __launch_bounds__(256)
+split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ rowscale, int64_t rows, int cols,
+               const float* __restrict__ amax, int fmt, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o) {
+    const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
+    const int64_t n4 = cols / 4;
+    const int64_t total = rows * n4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        const float s = scale * (rowscale ? __ldg(rowscale + r) : 1.f);
+        unsigned short h[4], l[4];
+        d16_split(v.x * s, fmt, h[0], l[0]); d16_split(v.y * s, fmt, h[1], l[1]);
+        d16_split(v.z * s, fmt, h[2], l[2]); d16_split(v.w * s, fmt, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + r * ld_o + c) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+        if (fmt == 0) *reinterpret_cast<uint2*>(lo + r * ld_o + c) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+    }
+}
+
+// gathered and transposed: hi/lo[c, s] = split(x[row_ids[s], c] * rowscale[row_ids[s]] * 2^k)   (side 0: H^T[dim, slots])
+__global__ void __launch_bounds__(256)
+split16_transpose_kernel(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__ row_ids, const float* __restrict__ rowscale,
+                         int64_t rows, int cols, const float* __restrict__ amax, int fmt,
+                         unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o) {
+    __shared__ float tile[32][33];
+    const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int64_t s0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t s = s0 + r;
+        float v = 0.f;
+        if (s < rows && c0 + tx < cols) {
+            const int64_t src = row_ids ? (int64_t)__ldg(row_ids + s) : s;
+            v = __ldg(x + src * ld + c0 + tx) * scale * (rowscale ? __ldg(rowscale + src) : 1.f);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+        const int64_t s = s0 + tx;
+        if (c0 + c < cols && s < rows) {
+            unsigned short h, l;
+            d16_split(tile[tx][c], fmt, h, l);
+            hi[(int64_t)(c0 + c) * ld_o + s] = h;
+            if (fmt == 0) lo[(int64_t)(c0 + c) * ld_o + s] = l;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (TMA store side; the load / MMA / TMEM wrappers are dense_tc.cuh's)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int x, int y) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MN-major operand, 64-byte swizzle: 32 contiguous MN elements per row, 8-row K atoms 512 B apart (SBO), the next
+// 32-element MN block one box further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
+    d |= (uint64_t)(kD16BoxMN >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                                    // SWIZZLE_64B
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16 (0) or bf16 (1), K-major or MN-major (both operands alike).
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n, int bf16, int mn_major) {
+    return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kD16TileM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct D16Params {
+    int side;                    // 0: cell destinations (K-major operands), 1: gene-slot destinations (MN-major operands)
+    int terms;                   // 3: hi*hi + lo*hi + hi*lo;  1: single product
+    int bf16;
+    int n, n_pad, n1, n2;        // output width, rounded up to 16, MMA N halves
+    int b_boxes, b_box_rows;     // side 0: TMA boxes covering the n_pad rows of B
+    int b_blocks;                // side 1: 32-column blocks of B
+    int stages, stage_bytes, tx_bytes, b_bytes;      // stage_bytes: ring pitch (1 KB multiple); tx_bytes: bytes TMA delivers per stage
+    int m_tiles;                 // destination tiles
+    int nb;                      // 32-slot gene blocks per cell tile of the storage
+    int num_kb, chunk_kb;        // k-blocks in all / per accumulation chain
+    int n_splits, kb_per_split;  // side 0: 1, num_kb
+    int64_t rows_per_split;      // side 1: rows of the output map per split (padded slots)
+    int64_t m_total;             // destination rows
+    const float* amax;           // device scalar the per-pass operand was scaled by, or null
+    float x_scale_inv;
+    const float* dscale;         // side 0 epilogue: out = dscale * acc + selfcoef * hself
+    const float* selfcoef;
+    const float* hself;
+    int64_t ld_hself;
+};
+
+__global__ void __launch_bounds__(kD16Threads, 1)
+dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_out, const D16Params p) {
+    extern __shared__ unsigned char dsmem_raw[];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* staging = ring + (size_t)p.stages * p.stage_bytes;          // 1024-byte aligned (stage_bytes % 1024 == 0)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kD16StagingBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kD16MaxStages;
+    uint64_t* tmem_full = bars + 2 * kD16MaxStages;
+    uint64_t* tmem_empty = bars + 2 * kD16MaxStages + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kD16MaxStages + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = p.m_tiles * p.n_splits;
+    const int a_planes = p.terms == 3 ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTcMaxN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------ TMA producer ------------------------------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int mt = item % p.m_tiles, split = item / p.m_tiles;
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    unsigned char* st = ring + (size_t)s * p.stage_bytes;
+                    unsigned char* sb = st + a_planes * kD16ABytes;
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
+                    if (p.side == 0) {
+                        const int row = (mt * p.nb + kb) * kD16TileM;          // cell tile mt, gene block kb: 8 KB contiguous
+                        tma_load_2d(st, &map_a_hi, 0, row, &full_bar[s]);
+                        if (p.terms == 3) tma_load_2d(st + kD16ABytes, &map_a_lo, 0, row, &full_bar[s]);
+                        for (int j = 0; j < p.b_boxes; ++j) {
+                            const int r0 = j * p.b_box_rows;
+                            tma_load_2d(sb + r0 * 64, &map_b_hi, kb * kD16BlockK, r0, &full_bar[s]);
+                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + r0 * 64, &map_b_lo, kb * kD16BlockK, r0, &full_bar[s]);
+                        }
+                    } else {
+                        // 32 cells of cell tile kb / 4, gene blocks 4 mt .. 4 mt + 3: four 2 KB pieces of one 32 KB region
+                        const int row = ((kb >> 2) * p.nb + 4 * mt) * kD16TileM + (kb & 3) * 32;
+                        for (int j = 0; j < 4; ++j) {
+                            tma_load_2d(st + j * kD16BoxMN, &map_a_hi, 0, row + j * kD16TileM, &full_bar[s]);
+                            if (p.terms == 3) tma_load_2d(st + kD16ABytes + j * kD16BoxMN, &map_a_lo, 0, row + j * kD16TileM, &full_bar[s]);
+                        }
+                        for (int j = 0; j < p.b_blocks; ++j) {
+                            tma_load_2d(sb + j * kD16BoxMN, &map_b_hi, j * 32, kb * kD16BlockK, &full_bar[s]);
+                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + j * kD16BoxMN, &map_b_lo, j * 32, kb * kD16BlockK, &full_bar[s]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------ MMA issuer --------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc_f16(p.n1, p.bf16, p.side);
+            const uint32_t idesc2 = umma_idesc_f16(p.n2 > 0 ? p.n2 : 16, p.bf16, p.side);
+            // advance along K by one MMA (16 elements): 32 bytes inside the 64-byte row (K-major) / two 8-row atoms (MN-major)
+            const uint64_t k_step = p.side == 0 ? (uint64_t)(32 >> 4) : (uint64_t)(1024 >> 4);
+            const uint64_t n2_off = p.side == 0 ? (uint64_t)((p.n1 * 64) >> 4) : (uint64_t)(((p.n1 / 32) * kD16BoxMN) >> 4);
+            int it = 0, chunk_no = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int split = item / p.m_tiles;
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb, ++chunk_no) {
+                    const int c1 = min(kb1, c0 + p.chunk_kb);
+                    mbar_wait(tmem_empty, (chunk_no & 1) ^ 1);             // the drain warps have emptied the accumulators
+                    tc_fence_after();
+                    for (int kb = c0; kb < c1; ++kb, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (it / p.stages) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        unsigned char* st = ring + (size_t)s * p.stage_bytes;
+                        unsigned char* sb = st + a_planes * kD16ABytes;
+                        uint64_t a_hi, a_lo, b_hi, b_lo;
+                        if (p.side == 0) {
+                            a_hi = umma_desc_sw64(st); a_lo = umma_desc_sw64(st + kD16ABytes);
+                            b_hi = umma_desc_sw64(sb); b_lo = umma_desc_sw64(sb + p.b_bytes);
+                        } else {
+                            a_hi = umma_desc_mn_sw64(st); a_lo = umma_desc_mn_sw64(st + kD16ABytes);
+                            b_hi = umma_desc_mn_sw64(sb); b_lo = umma_desc_mn_sw64(sb + p.b_bytes);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < kD16BlockK / kD16UmmaK; ++kk) {
+                            const uint64_t ko = (uint64_t)kk * k_step;
+                            const uint32_t acc0 = (kb != c0 || kk != 0) ? 1u : 0u;
+                            tc_mma_f16(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
+                            if (p.terms == 3) {
+                                tc_mma_f16(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
+                                tc_mma_f16(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                            }
+                            if (p.n2 > 0) {
+                                tc_mma_f16(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
+                                if (p.terms == 3) {
+                                    tc_mma_f16(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
+                                    tc_mma_f16(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                                }
+                            }
+                        }
+                        tc_commit(&empty_bar[s]);
+                    }
+                    tc_commit(tmem_full);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------ drain warps -------------------------------------
+        const int q = warp & 3;                                   // TMEM lane quarter of this warp
+        unsigned char* my_stage = staging + (warp - 2) * (2 * 32 * 64);
+        const int sw = (lane >> 1) & 3;                           // 64-byte swizzle: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
+        float h_inv = p.x_scale_inv;
+        if (p.amax) h_inv *= ldexpf(1.f, -d16_scale_exp(*p.amax));
+        int chunk_no = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int mt = item % p.m_tiles, split = item / p.m_tiles;
+            const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+            const int64_t grow = (int64_t)mt * kD16TileM + q * 32 + lane;        // destination row of this thread
+            const int out_row = (int)(split * p.rows_per_split + (int64_t)mt * kD16TileM + q * 32);
+            const bool row_ok = grow < p.m_total;
+            float scale = h_inv, sc = 0.f;
+            if (p.side == 0 && row_ok) {
+                if (p.dscale) scale *= __ldg(p.dscale + grow);
+                if (p.selfcoef) sc = __ldg(p.selfcoef + grow);
+            }
+            for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb, ++chunk_no) {
+                const bool first = c0 == kb0;
+                mbar_wait(tmem_full, chunk_no & 1);
+                tc_fence_after();
+                // the previous chain's adds to these rows have been performed (and the staging buffers are free)
+                if (lane == 0) bulk_wait_all();
+                __syncwarp();
+                for (int cb = 0; cb * kD16OutCols < p.n_pad; ++cb) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * kD16OutCols), v);
+                    if (cb >= 2) {                                       // the store issued two blocks ago has read this buffer
+                        if (lane == 0) bulk_wait_read_1();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] *= scale;
+                    if (first && p.selfcoef != nullptr && p.side == 0 && row_ok) {
+                        const float* hrow = p.hself + grow * p.ld_hself + cb * kD16OutCols;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (cb * kD16OutCols + j * 4 < p.n) {
+                                const float4 h = __ldg(reinterpret_cast<const float4*>(hrow + j * 4));
+                                v[j * 4 + 0] = fmaf(sc, h.x, v[j * 4 + 0]); v[j * 4 + 1] = fmaf(sc, h.y, v[j * 4 + 1]);
+                                v[j * 4 + 2] = fmaf(sc, h.z, v[j * 4 + 2]); v[j * 4 + 3] = fmaf(sc, h.w, v[j * 4 + 3]);
+                            }
+                        }
+                    }
+                    unsigned char* buf = my_stage + (cb & 1) * (32 * 64);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ sw) << 4)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (first) tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row);
+                        else tma_reduce_add_2d(&map_out, buf, cb * kD16OutCols, out_row);
+                        bulk_commit_group();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcMaxN));
+    }
+}
+
+// Sum of the side-1 split partials (+ the tiled kernel's epilogue) when the CSR remainder of the pass is empty:
+// one warp per destination row; slot = map[v] (< 0: the row has no dense entries) or v.
+__global__ void __launch_bounds__(256)
+dense16_finalize_kernel(const TiledParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t v = warp0; v < p.n_dst; v += nwarps) {
+        RowAcc<0> acc;
+        acc.zero();
+        const int64_t slot = p.init_map ? (int64_t)__ldg(p.init_map + v) : v;
+        if (slot >= 0) {
+            for (int s = 0; s < p.init_slabs; ++s) {
+                const float* src = p.init + ((size_t)s * p.init_rows + slot) * p.dim;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = (j * 32 + lane) * 4;
+                    if (c < p.dim) {
+                        const float4 t = *reinterpret_cast<const float4*>(src + c);
+                        acc.v4[j].x += t.x; acc.v4[j].y += t.y; acc.v4[j].z += t.z; acc.v4[j].w += t.w;
+                    }
+                }
+            }
+        }
+        tiled_row_epilogue<0>(p, v, acc, lane);
+    }
+}
+
+// ------------------------------------------ host side ------------------------------------------
+inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
+                       uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_rows, const char* what) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(WSAGE_ECUDA, "%s: %s", what, "cuTensorMapEncodeTiled not available");
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    (void)elem_bytes;
+    const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WSAGE_ECUDA, "%s: %s", what, "cuTensorMapEncodeTiled failed");
+    return WSAGE_OK;
+}
+
+inline int d16_slots_pad(int gene_slots) { return (gene_slots + kD16TileM - 1) / kD16TileM * kD16TileM; }
+
+struct D16Plan {
+    int m_tiles, nb, num_kb, chunk_kb, n_splits, kb_per_split;
+    int n_pad, n1, n2, b_boxes, b_box_rows, b_blocks, b_bytes, stage_bytes, tx_bytes, stages;
+    size_t smem_bytes;
+};
+
+// side 1: cut the cell range into splits of whole chains so that the (tile, split) items fill the 148 SMs evenly
+inline void d16_choose_splits(int m_tiles, int num_kb, int chunk_kb, int& n_splits, int& kb_per_split) {
+    const int chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+    int best = 1;
+    double best_eff = -1.0;
+    const int max_splits = chunks < 64 ? chunks : 64;
+    for (int s = 1; s <= max_splits; ++s) {
+        const int cps = (chunks + s - 1) / s;
+        const int ns = (chunks + cps - 1) / cps;
+        if (ns != s) continue;
+        const int64_t items = (int64_t)m_tiles * ns;
+        const int64_t rounds = (items + kNumSMs - 1) / kNumSMs;
+        const double eff = (double)m_tiles * chunks / ((double)kNumSMs * rounds * cps);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }           // fewer splits unless clearly better
+    }
+    const int cps = (chunks + best - 1) / best;
+    n_splits = (chunks + cps - 1) / cps;
+    kb_per_split = cps * chunk_kb;
+}
+
+inline int d16_plan(const wsage_dense16_args* a, D16Plan& pl) {
+    const int terms = a->fmt == WSAGE_D16_F16X2 ? 3 : 1;
+    pl.nb = d16_slots_pad(a->gene_slots) / kD16BlockK;
+    int chunk_rows = a->chunk_rows > 0 ? a->chunk_rows : kD16DefaultChunkRows;
+    pl.chunk_kb = (chunk_rows + kD16BlockK - 1) / kD16BlockK;
+    pl.n_pad = (a->dim + 15) & ~15;
+    pl.n1 = pl.n_pad < 256 ? pl.n_pad : 256;
+    pl.n2 = pl.n_pad - pl.n1;
+    pl.b_boxes = (pl.n_pad + 255) / 256;
+    pl.b_box_rows = pl.n_pad / pl.b_boxes;
+    pl.b_blocks = (pl.n_pad + 31) / 32;
+    if (a->side == 0) {
+        pl.m_tiles = (int)((a->n_dst + kD16TileM - 1) / kD16TileM);
+        pl.num_kb = (a->gene_slots + kD16BlockK - 1) / kD16BlockK;
+        pl.n_splits = 1;
+        pl.kb_per_split = pl.num_kb;
+        pl.b_bytes = pl.n_pad * 64;
+    } else {
+        pl.m_tiles = d16_slots_pad(a->gene_slots) / kD16TileM;
+        pl.num_kb = (int)((a->n_src_cells + kD16BlockK - 1) / kD16BlockK);
+        d16_choose_splits(pl.m_tiles, pl.num_kb, pl.chunk_kb, pl.n_splits, pl.kb_per_split);
+        pl.b_bytes = pl.b_blocks * kD16BoxMN;
+    }
+    pl.tx_bytes = (terms == 3 ? 2 : 1) * (kD16ABytes + pl.b_bytes);
+    pl.stage_bytes = (pl.tx_bytes + 1023) & ~1023;
+    const int fixed = kD16StagingBytes + 256 + 1024;
+    pl.stages = (kD16SmemBudget - fixed) / pl.stage_bytes;
+    if (pl.stages > kD16MaxStages) pl.stages = kD16MaxStages;
+    pl.smem_bytes = (size_t)pl.stages * pl.stage_bytes + fixed;
+    return WSAGE_OK;
+}
+
+}  // namespace wsage

@@ -1,8 +1,8 @@
 // extern "C" entry points of libwsage.so (declared in include/wsage.h).
 #include "agg_gather.cuh"
 #include "agg_tiled.cuh"
-#include "agg_dense.cuh"
 #include "dense_tc.cuh"
+#include "dense16.cuh"
 #include "sampler.cuh"
 #include "loss_adam.cuh"
 #include <math.h>
@@ -11,9 +11,7 @@ using namespace wsage;
 
 extern "C" {
 
-int wsage_version(void) { return 1001; }
-
-int wsage_dense_tile(void) { return kDenseT; }
+int wsage_version(void) { return 2000; }
 
 const char* wsage_last_error(void) { return g_err; }
 
@@ -79,12 +77,11 @@ static int spmm_validate(const wsage_spmm_args* a) {
     WSAGE_REQUIRE(!a->dot || (a->q && a->ld_q >= a->dim), "dot needs q");
     WSAGE_REQUIRE(!a->out || a->ld_out >= a->dim, "ld_out < dim");
     WSAGE_REQUIRE(!a->raw || a->ld_raw >= a->dim, "ld_raw < dim");
-    if (a->dense_x) {
-        WSAGE_REQUIRE(a->dense_k > 0 && a->dense_t > 0, "dense block needs dense_k, dense_t > 0");
-        WSAGE_REQUIRE(a->dense_src_ids || a->dense_k == a->n_src, "dense_src_ids == NULL needs dense_k == n_src");
-        WSAGE_REQUIRE(a->dense_dst_map || a->dense_t == a->n_dst, "dense_dst_map == NULL needs dense_t == n_dst");
-        WSAGE_REQUIRE(aligned16(a->dense_x), "dense_x must be 16-byte aligned");
-        WSAGE_REQUIRE(a->algo != 1, "a dense block needs the tiled kernel (algo 0 or 2)");
+    if (a->init) {
+        WSAGE_REQUIRE(a->init_slabs > 0 && a->init_rows > 0, "init needs init_slabs, init_rows > 0");
+        WSAGE_REQUIRE(a->init_map || a->init_rows >= a->n_dst, "init_map == NULL needs init_rows >= n_dst");
+        WSAGE_REQUIRE(aligned16(a->init), "init must be 16-byte aligned");
+        WSAGE_REQUIRE(a->algo != 1, "init needs the tiled kernel (algo 0 or 2)");
     }
     return WSAGE_OK;
 }
@@ -97,26 +94,30 @@ static bool spmm_vec4(const wsage_spmm_args* a) {
            (!a->q || (a->ld_q % 4 == 0 && aligned16(a->q)));
 }
 
-// workspace = [tiled split partials, rounded up to 256 B][dense block sums]
-static size_t spmm_tiled_ws(const wsage_spmm_args* a, bool vec4) {
-    const bool tiled = dense_requested(a) ? tiled_supported(a, vec4) : (a->algo == 2 || (a->algo == 0 && tiled_profitable(a, vec4)));
-    if (!tiled || !tiled_supported(a, vec4)) return 0;
-    return (tiled_plan(a).workspace_bytes + 255) & ~(size_t)255;
+static bool spmm_use_tiled(const wsage_spmm_args* a, bool vec4) {
+    if (a->init) return a->nnz > 0;
+    return a->algo == 2 || (a->algo == 0 && tiled_profitable(a, vec4));
 }
 
 size_t wsage_spmm_workspace_bytes(const wsage_spmm_args* a) {
     if (!a || spmm_validate(a) != WSAGE_OK || a->n_dst == 0) return 0;
     const bool vec4 = spmm_vec4(a);
-    size_t n = spmm_tiled_ws(a, vec4);
-    if (dense_requested(a) && tiled_supported(a, vec4)) n += dense_plan(a).out_bytes;
-    return n;
+    if (!spmm_use_tiled(a, vec4) || !tiled_supported(a, vec4)) return 0;
+    return tiled_plan(a).workspace_bytes;
 }
 
 int wsage_spmm_algo(const wsage_spmm_args* a) {
     if (!a || spmm_validate(a) != WSAGE_OK) return 0;
     if (a->algo != 0) return a->algo;
-    if (dense_requested(a)) return 2;
+    if (a->init) return 2;
     return tiled_profitable(a, spmm_vec4(a)) ? 2 : 1;
+}
+
+static void fill_epilogue(TiledParams& p, const wsage_spmm_args* a) {
+    p.n_dst = a->n_dst; p.dim = a->dim;
+    p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
+    p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
+    p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot;
 }
 
 int wsage_spmm(const wsage_spmm_args* a, void* stream) {
@@ -125,23 +126,25 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream) {
     if (a->n_dst == 0) return WSAGE_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = spmm_vec4(a);
+    if (a->init && !(vec4 && a->dim <= 512))
+        return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "init needs dim % 4 == 0, dim <= 512 and 16-byte aligned rows");
+    if (a->init && a->nnz == 0) {
+        // every entry of the pass sits in the dense block: sum its slabs, apply the epilogue
+        TiledParams p{};
+        fill_epilogue(p, a);
+        p.init = a->init; p.init_slabs = a->init_slabs; p.init_rows = a->init_rows; p.init_map = a->init_map;
+        dense16_finalize_kernel<<<gather_grid(a->n_dst), 256, 0, st>>>(p);
+        return check_launch("dense16_finalize");
+    }
     int algo = a->algo;
-    if (algo == 0) algo = (dense_requested(a) || tiled_profitable(a, vec4)) ? 2 : 1;
+    if (algo == 0) algo = (a->init || tiled_profitable(a, vec4)) ? 2 : 1;
     if (algo == 2) {
         if (!tiled_supported(a, vec4))
             return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_spmm", "tiled kernel needs dim % 4 == 0, contiguous 16-byte aligned hs and dim <= 512");
-        const size_t tiled_ws = spmm_tiled_ws(a, vec4);
-        const size_t need = tiled_ws + (dense_requested(a) ? dense_plan(a).out_bytes : 0);
+        const size_t need = tiled_plan(a).workspace_bytes;
         if (need > a->workspace_bytes || (need && !a->workspace))
             return fail(WSAGE_EINVAL, "%s: %s", "wsage_spmm", "workspace too small (see wsage_spmm_workspace_bytes)");
-        TiledInit ini{nullptr, 0, 0, nullptr};
-        if (dense_requested(a)) {
-            const DensePlan dp = dense_plan(a);
-            float* dout = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + tiled_ws);
-            const int rc2 = launch_dense(a, dp, dout, st);
-            if (rc2 != WSAGE_OK) return rc2;
-            ini = TiledInit{dout, dp.n_splits, a->dense_t, a->dense_dst_map};
-        }
+        const TiledInit ini{a->init, a->init ? a->init_slabs : 0, a->init_rows, a->init_map};
         return launch_tiled(a, ini, st);
     }
     GatherParams p{};
@@ -152,6 +155,131 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream) {
     p.q = a->q; p.ld_q = a->ld_q; p.dot = a->dot; p.row_perm = a->row_perm;
     return a->col_bits == WSAGE_COL_U16 ? launch_gather_fwd<uint16_t, false>(p, vec4, st)
                                         : launch_gather_fwd<int32_t, false>(p, vec4, st);
+}
+
+// ---- dense block of the popular genes on the tensor cores ---------------------------------------------------------
+int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
+               int64_t rows, int32_t cols, float* amax, void* stream) {
+    WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
+    WSAGE_REQUIRE(amax, "null amax");
+    if (rows == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(x && ld >= cols && ld % 4 == 0 && aligned16(x), "x must be 16-byte aligned with ld % 4 == 0");
+    const int64_t total = rows * (cols / 4);
+    int64_t grid = (total + 255) / 256;
+    if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
+    amax_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, row_ids, rowscale, rows, cols, reinterpret_cast<unsigned*>(amax));
+    return check_launch("amax");
+}
+
+int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
+                  int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t transpose,
+                  void* hi, void* lo, int64_t ld_out, void* stream) {
+    WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
+    WSAGE_REQUIRE(fmt == WSAGE_D16_F16X2 || fmt == WSAGE_D16_BF16, "unknown fmt");
+    if (rows == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(x && hi && (lo || fmt == WSAGE_D16_BF16), "null pointer");
+    WSAGE_REQUIRE(ld >= cols && ld % 4 == 0 && aligned16(x), "x must be 16-byte aligned with ld % 4 == 0");
+    WSAGE_REQUIRE(ld_out % 8 == 0 && aligned16(hi) && aligned16(lo), "planes must be 16-byte aligned with ld_out % 8 == 0");
+    WSAGE_REQUIRE(ld_out >= (transpose ? rows : (int64_t)cols), "ld_out too small");
+    WSAGE_REQUIRE(transpose || !row_ids, "row_ids needs transpose");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned short* h = static_cast<unsigned short*>(hi);
+    unsigned short* l = static_cast<unsigned short*>(lo);
+    if (transpose) {
+        WSAGE_REQUIRE(rows < ((int64_t)1 << 31) * 32, "too many rows");
+        dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+        split16_transpose_kernel<<<grid, 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out);
+        return check_launch("split16_transpose");
+    }
+    const int64_t total = rows * (cols / 4);
+    int64_t grid = (total + 255) / 256;
+    if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
+    split16_kernel<<<(int)grid, 256, 0, st>>>(x, ld, rowscale, rows, cols, amax, fmt, h, l, ld_out);
+    return check_launch("split16");
+}
+
+int wsage_dense16_slots_pad(int32_t gene_slots) { return gene_slots > 0 ? d16_slots_pad(gene_slots) : 0; }
+
+static int dense16_validate(const wsage_dense16_args* a, bool need_out = true) {
+    WSAGE_REQUIRE(a != nullptr, "null args");
+    WSAGE_REQUIRE(a->fmt == WSAGE_D16_F16X2 || a->fmt == WSAGE_D16_BF16, "unknown fmt");
+    WSAGE_REQUIRE(a->side == 0 || a->side == 1, "side must be 0 or 1");
+    WSAGE_REQUIRE(a->cells > 0 && a->gene_slots > 0 && a->dim > 0, "cells, gene_slots and dim must be positive");
+    WSAGE_REQUIRE(a->dim % 4 == 0 && a->dim <= kTcMaxN, "dim must be a multiple of 4, at most 512");
+    WSAGE_REQUIRE(a->x_hi && (a->x_lo || a->fmt == WSAGE_D16_BF16) && a->h_hi && (a->h_lo || a->fmt == WSAGE_D16_BF16) && (a->out || !need_out), "null pointer");
+    WSAGE_REQUIRE(a->x_scale > 0.f, "x_scale must be positive");
+    WSAGE_REQUIRE(a->ld_h % 8 == 0 && aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned with ld_h % 8 == 0");
+    WSAGE_REQUIRE(aligned16(a->x_hi) && aligned16(a->x_lo) && aligned16(a->out), "X planes and out must be 16-byte aligned");
+    WSAGE_REQUIRE(a->chunk_rows >= 0, "negative chunk_rows");
+    if (a->side == 0) {
+        WSAGE_REQUIRE(a->n_dst > 0 && a->n_dst <= a->cells, "side 0 needs 0 < n_dst <= cells");
+        WSAGE_REQUIRE(a->ld_h >= a->gene_slots, "side 0: ld_h < gene_slots");
+        WSAGE_REQUIRE(a->ld_out >= a->dim && a->ld_out % 4 == 0, "ld_out must be >= dim and a multiple of 4");
+        WSAGE_REQUIRE(!a->selfcoef || (a->hself && a->ld_hself >= a->dim && a->ld_hself % 4 == 0 && aligned16(a->hself)), "selfcoef needs a 16-byte aligned hself");
+    } else {
+        WSAGE_REQUIRE(a->n_src_cells > 0 && a->n_src_cells <= a->cells, "side 1 needs 0 < n_src_cells <= cells");
+        WSAGE_REQUIRE(a->ld_h >= a->dim, "side 1: ld_h < dim");
+        WSAGE_REQUIRE(!a->dscale && !a->selfcoef, "side 1 writes raw partial sums (epilogue in wsage_spmm)");
+    }
+    const int64_t storage_rows = ((a->cells + kD16TileM - 1) / kD16TileM) * (d16_slots_pad(a->gene_slots) / kD16BlockK) * kD16TileM;
+    WSAGE_REQUIRE(storage_rows < ((int64_t)1 << 31), "dense block too large for 32-bit TMA coordinates");
+    return WSAGE_OK;
+}
+
+int wsage_dense16_splits(const wsage_dense16_args* a) {
+    if (dense16_validate(a, false) != WSAGE_OK) return 0;
+    D16Plan pl{};
+    d16_plan(a, pl);
+    return pl.n_splits;
+}
+
+int wsage_dense16(const wsage_dense16_args* a, void* stream) {
+    int rc = dense16_validate(a);
+    if (rc != WSAGE_OK) return rc;
+    D16Plan pl{};
+    d16_plan(a, pl);
+    if (pl.stages < 2) return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_dense16", "dim too large for a two-stage shared-memory ring");
+    const bool bf = a->fmt == WSAGE_D16_BF16;
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const int slots_pad = d16_slots_pad(a->gene_slots);
+    const uint64_t storage_rows = (uint64_t)((a->cells + kD16TileM - 1) / kD16TileM) * (uint64_t)pl.nb * kD16TileM;
+    const void* x_lo = bf ? a->x_hi : a->x_lo;
+    const void* h_lo = bf ? a->h_hi : a->h_lo;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mo;
+    const char* what = "wsage_dense16";
+    D16Params p{};
+    p.side = a->side; p.terms = bf ? 1 : 3; p.bf16 = bf ? 1 : 0;
+    p.n = a->dim; p.n_pad = pl.n_pad; p.n1 = pl.n1; p.n2 = pl.n2;
+    p.b_boxes = pl.b_boxes; p.b_box_rows = pl.b_box_rows; p.b_blocks = pl.b_blocks;
+    p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tx_bytes = pl.tx_bytes; p.b_bytes = pl.b_bytes;
+    p.m_tiles = pl.m_tiles; p.nb = pl.nb; p.num_kb = pl.num_kb; p.chunk_kb = pl.chunk_kb;
+    p.n_splits = pl.n_splits; p.kb_per_split = pl.kb_per_split;
+    p.amax = bf ? nullptr : a->h_amax;
+    p.x_scale_inv = 1.f / a->x_scale;
+    if (a->side == 0) {
+        if ((rc = make_map_2d(&ma_hi, dt, 2, a->x_hi, 32, storage_rows, 64, 32, kD16TileM, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_2d(&ma_lo, dt, 2, x_lo, 32, storage_rows, 64, 32, kD16TileM, what)) != WSAGE_OK) return rc;
+        // B = H^T [dim][gene_slots]: columns past gene_slots and rows past dim are zero-filled by TMA
+        if ((rc = make_map_2d(&mb_hi, dt, 2, a->h_hi, (uint64_t)a->gene_slots, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.b_box_rows, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_2d(&mb_lo, dt, 2, h_lo, (uint64_t)a->gene_slots, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.b_box_rows, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_2d(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->dim, (uint64_t)a->n_dst, (uint64_t)a->ld_out * 4, kD16OutCols, 32, what)) != WSAGE_OK) return rc;
+        p.rows_per_split = 0; p.m_total = a->n_dst;
+        p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
+    } else {
+        if ((rc = make_map_2d(&ma_hi, dt, 2, a->x_hi, 32, storage_rows, 64, 32, 32, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_2d(&ma_lo, dt, 2, x_lo, 32, storage_rows, 64, 32, 32, what)) != WSAGE_OK) return rc;
+        // B = H [n_src_cells][dim]: rows past n_src_cells and columns past dim are zero-filled by TMA
+        if ((rc = make_map_2d(&mb_hi, dt, 2, a->h_hi, (uint64_t)a->dim, (uint64_t)a->n_src_cells, (uint64_t)a->ld_h * 2, 32, 32, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_2d(&mb_lo, dt, 2, h_lo, (uint64_t)a->dim, (uint64_t)a->n_src_cells, (uint64_t)a->ld_h * 2, 32, 32, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_2d(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->dim, (uint64_t)pl.n_splits * slots_pad, (uint64_t)a->dim * 4, kD16OutCols, 32, what)) != WSAGE_OK) return rc;
+        p.rows_per_split = slots_pad; p.m_total = slots_pad;
+    }
+    cudaError_t e = cudaFuncSetAttribute(dense16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(dense16)", cudaGetErrorString(e));
+    const int64_t items = (int64_t)pl.m_tiles * pl.n_splits;
+    const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+    dense16_kernel<<<grid, kD16Threads, pl.smem_bytes, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
+    return check_launch("dense16");
 }
 
 int wsage_split_tf32(const float* x, int64_t ld_x, const float* mask_src, int64_t ld_mask,

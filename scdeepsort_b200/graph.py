@@ -73,6 +73,9 @@ class DeepSortGraph:
         (utils/preprocess_internal.py:15-23,170-173,211-214) for atlases whose edge list never exists on the
         host.  Every cell must be a support cell.  ``in_src`` is int32 (N < 2^31) to halve its footprint."""
         assert bg.num_support == bg.num_cells, "test cells (gene->cell only) need the host builder"
+        if getattr(bg, "densified", False) or bg.cell_csr.dense is not None or bg.gene_csr.dense is not None:
+            raise ValueError("DeepSortGraph.from_bipartite needs the complete CSRs: build it before BipartiteGraph.densify() "
+                             "(a densified graph keeps the popular genes' edges outside the CSRs)")
         dev, g, c = bg.device, bg.num_genes, bg.num_cells
         n = g + c
 
@@ -177,31 +180,18 @@ def _to_csr(rowptr, col, x, n_src, n_dst, device):
                n_src, n_dst, bits, _balanced_row_perm(deg).to(device))
 
 
-def _split_dense(csr: Csr, slot: torch.Tensor, side: str, tile: int, chunk_edges: int = 1 << 27) -> Csr:
-    """Moves the entries of the popular genes (``slot[gene] >= 0``) out of ``csr`` into a ``DenseBlock``.
+def _strip_dense(csr: Csr, slot: torch.Tensor, side: str, fill=None, chunk_edges: int = 1 << 27) -> Csr:
+    """Removes the entries of the popular genes (``slot[gene] >= 0``) from ``csr``.
 
-    side == 'src': the genes are the COLUMNS of csr (cell-destination CSR); the block's sources are the
-    popular genes, its destinations every row.  side == 'dst': the genes are the ROWS (gene-destination
-    CSR); the block's sources are every column (cell), its destinations the popular genes' slots.
+    side == 'src': the genes are the COLUMNS of csr (cell-destination CSR); side == 'dst': the genes are the ROWS
+    (gene-destination CSR).  ``fill(row, slot, x)`` receives the removed entries (side 'src' only: row = cell).
     Works in row chunks so the index temporaries stay bounded at atlas scale."""
     dev = csr.x.device
-    md = int((slot >= 0).sum())
     n_dst, n_src = csr.n_dst, csr.n_src
-    if side == 'src':
-        k, t = md, n_dst
-        ids = torch.nonzero(slot >= 0).flatten()
-        order = torch.argsort(slot[ids])
-        src_ids, dst_map = ids[order].to(torch.int32), None
-    else:
-        k, t = n_src, md
-        src_ids, dst_map = None, slot.to(torch.int32)
-    n_tiles = (t + tile - 1) // tile
-    xd = torch.zeros(n_tiles * k * tile, dtype=torch.float32, device=dev)
     rowptr_h = csr.rowptr.cpu()
     deg = csr.rowptr[1:] - csr.rowptr[:-1]
     new_deg = torch.zeros(n_dst, dtype=torch.int64, device=dev)
     cols, vals = [], []
-    moved = 0
     r0 = 0
     while r0 < n_dst:
         # largest r1 with rowptr[r1] - rowptr[r0] <= chunk_edges (at least one row)
@@ -209,33 +199,68 @@ def _split_dense(csr: Csr, slot: torch.Tensor, side: str, tile: int, chunk_edges
         r1 = min(max(r1, r0 + 1), n_dst)
         e0, e1 = int(rowptr_h[r0]), int(rowptr_h[r1])
         if e1 > e0:
-            col = csr.col[e0:e1].to(torch.int64)
-            if csr.col_bits == _lib.COL_U16:
-                col = col & 0xFFFF
             row = torch.repeat_interleave(torch.arange(r0, r1, device=dev), deg[r0:r1], output_size=e1 - e0)
             x = csr.x[e0:e1]
             if side == 'src':
+                col = csr.col[e0:e1].to(torch.int64)
+                if csr.col_bits == _lib.COL_U16:
+                    col = col & 0xFFFF
                 s_e = slot[col]
-                hit = s_e >= 0
-                idx = ((row[hit] // tile) * k + s_e[hit]) * tile + row[hit] % tile
+                del col
             else:
                 s_e = slot[row]
-                hit = s_e >= 0
-                idx = ((s_e[hit] // tile) * k + col[hit]) * tile + s_e[hit] % tile
-            xd[idx] = x[hit]
-            moved += int(hit.sum())
+            hit = s_e >= 0
+            if fill is not None:
+                fill(row[hit], s_e[hit], x[hit])
             keep = ~hit
             cols.append(csr.col[e0:e1][keep])
             vals.append(x[keep])
             new_deg[r0:r1] = torch.zeros(r1 - r0, dtype=torch.int64, device=dev).index_add_(0, row - r0, keep.to(torch.int64))
-            del col, row, s_e, hit, idx, keep
+            del row, s_e, hit, keep
         r0 = r1
     rp = torch.zeros(n_dst + 1, dtype=torch.int64, device=dev)
     rp[1:] = torch.cumsum(new_deg, 0)
     col_new = torch.cat(cols) if cols else csr.col[:0]
     x_new = torch.cat(vals) if vals else csr.x[:0]
-    return Csr(rp, col_new, x_new, n_src, n_dst, csr.col_bits, _balanced_row_perm(new_deg),
-               DenseBlock(xd, k, t, src_ids, dst_map, moved))
+    return Csr(rp, col_new, x_new, n_src, n_dst, csr.col_bits, _balanced_row_perm(new_deg))
+
+
+def _build_dense_block(cell_csr: Csr, slot: torch.Tensor, gene_ids: torch.Tensor, fmt: int):
+    """(stripped cell-destination CSR, DenseBlock): the popular genes' entries of every cell as 16-bit planes
+    ``plane[cell // 128][slot // 32][cell % 128][slot % 32]`` (include/wsage.h).  fp16 hi + lo of x * 2^k with
+    max|x| * 2^k in [2^13, 2^14) (fp32-grade), or bf16(x) (BASELINE configs[2])."""
+    dev = cell_csr.x.device
+    lib = _lib.load()
+    n_cells, gd = cell_csr.n_dst, int(gene_ids.numel())
+    slots_pad = int(lib.wsage_dense16_slots_pad(gd))
+    nb = slots_pad // 32
+    n_tiles = (n_cells + 127) // 128
+    numel = n_tiles * nb * 128 * 32
+    f16 = fmt == _lib.D16_F16X2
+    x_scale = 1.0
+    if f16 and cell_csr.nnz:
+        xmax = float(cell_csr.x.abs().max())
+        if xmax > 0 and np.isfinite(xmax):
+            x_scale = float(2.0 ** (14 - np.frexp(xmax)[1]))
+    hi = torch.zeros(numel, dtype=torch.float16 if f16 else torch.bfloat16, device=dev)
+    lo = torch.zeros(numel, dtype=torch.float16, device=dev) if f16 else None
+    moved = [0]
+
+    def fill(row, s, x):
+        idx = (((row // 128) * nb + s // 32) * 128 + row % 128) * 32 + s % 32
+        if f16:
+            v = x * x_scale
+            h = v.to(torch.float16)
+            hi[idx] = h
+            lo[idx] = (v - h.to(torch.float32)).to(torch.float16)
+        else:
+            hi[idx] = x.to(torch.bfloat16)
+        moved[0] += int(x.numel())
+
+    stripped = _strip_dense(cell_csr, slot, 'src', fill)
+    block = DenseBlock(hi.view(torch.int16), lo.view(torch.int16) if lo is not None else None, fmt, n_cells, gd, slots_pad,
+                       gene_ids.to(torch.int32).contiguous(), slot.to(torch.int32).contiguous(), x_scale, moved[0])
+    return stripped, block
 
 
 @dataclass
@@ -287,28 +312,27 @@ class BipartiteGraph:
             out.cell_csr_t = _to_csr(xt.indptr, xt.indices, xt.data, xa.shape[0], g, device)
         return out
 
-    def densify(self, threshold: float = 0.3, max_bytes: int = 32 << 30, directions=("gene",)) -> "BipartiteGraph":
+    def densify(self, threshold: float = 0.05, max_bytes: int = 96 << 30, fmt: str = "f16x2") -> "BipartiteGraph":
         """Splits X = X_sparse + X_dense IN PLACE for the full-graph path: genes expressed in at least
-        ``threshold`` of the (local) support cells leave the CSRs and become zero-filled dense blocks
-        (``Csr.dense``), which wsage_spmm runs on the FMA-bound dense-block kernel before the CSR walk.
-        Results are unchanged up to fp32 summation order.  The popular set is capped so that the blocks
-        stay within ``max_bytes``.  ``directions``: "gene" splits the gene-destination CSR(s) (whole dense
-        destination tiles leave the CSR walk, whose remaining tiles are unaffected: the profitable case),
-        "cell" also splits the cell-destination CSR (every row gets thinner, which costs the CSR walk
-        efficiency: measured no gain at 10 % density, kept for denser atlases).  Not for the mini-batch
-        surface (``DeepSortGraph.from_bipartite`` needs the complete CSRs)."""
+        ``threshold`` of the (local) support cells leave every CSR and become ONE zero-filled block of 16-bit
+        tiles (``Csr.dense``, shared by all directions) that wsage_dense16 runs on the tensor cores before the
+        CSR walk — for such a gene, multiplying through its zeros on tcgen05 is cheaper than walking its edges.
+        ``fmt``: "f16x2" (fp16 hi + lo, three products: results agree with the plain CSR path to fp32 rounding)
+        or "bf16" (one product; BASELINE configs[2]).  The popular set is capped so that the planes stay within
+        ``max_bytes``.  A gene set that covers every entry leaves empty CSRs (wsage_spmm then only reduces).
+        Not for the mini-batch surface: ``DeepSortGraph.from_bipartite`` needs the complete CSRs and refuses a
+        densified graph."""
         if getattr(self, "densified", False) or self.gene_csr.n_src == 0 or self.nnz == 0:
             return self
+        fmt_id = {"f16x2": _lib.D16_F16X2, "bf16": _lib.D16_BF16}[fmt]
         dev = self.device
         gcsr = self.gene_csr
         deg_g = (gcsr.rowptr[1:] - gcsr.rowptr[:-1])
         rho = deg_g.to(torch.float64) / float(gcsr.n_src)
-        cand = torch.nonzero(rho >= threshold).flatten()
-        do_gene, do_cell = "gene" in directions, "cell" in directions
-        n_blocks = (int(do_gene) * (2 if self.cell_csr_t is not None else 1)) + int(do_cell)
-        if n_blocks == 0:
-            return self
-        cap = int(max_bytes // (4 * n_blocks * max(1, self.num_cells)))
+        cand = torch.nonzero((rho >= threshold) & (deg_g > 0)).flatten()
+        planes = 2 if fmt_id == _lib.D16_F16X2 else 1
+        cells_pad = (self.num_cells + 127) // 128 * 128
+        cap = int(max_bytes // (2 * planes * max(1, cells_pad))) // 128 * 128
         if cand.numel() > cap:                       # keep the most popular ones
             cand = cand[torch.argsort(deg_g[cand], descending=True)[:cap]]
             cand = torch.sort(cand).values
@@ -316,18 +340,33 @@ class BipartiteGraph:
             return self
         slot = torch.full((self.num_genes,), -1, dtype=torch.int64, device=dev)
         slot[cand] = torch.arange(cand.numel(), device=dev)
-        tile = int(_lib.load().wsage_dense_tile())
-        new_cell = _split_dense(self.cell_csr, slot, 'src', tile) if do_cell else self.cell_csr
-        new_gene = _split_dense(self.gene_csr, slot, 'dst', tile) if do_gene else self.gene_csr
+        new_cell, block = _build_dense_block(self.cell_csr, slot, cand, fmt_id)
+        new_cell.dense, new_cell.dense_side = block, 0
+        new_gene = _strip_dense(self.gene_csr, slot, 'dst')
+        new_gene.dense, new_gene.dense_side = block, 1
         new_t = self.cell_csr_t
-        if do_gene and new_t is not None:
-            new_t = _split_dense(new_t, slot, 'dst', tile)
-        if new_cell.nnz == 0 or new_gene.nnz == 0 or (new_t is not None and new_t.nnz == 0):
-            return self                              # the CSR walk needs a non-empty remainder
+        if new_t is not None:
+            new_t = _strip_dense(new_t, slot, 'dst')
+            new_t.dense, new_t.dense_side = block, 1
         self.cell_csr, self.gene_csr, self.cell_csr_t = new_cell, new_gene, new_t
         self.densified = True
         self.dense_genes = cand
         return self
+
+    def support_cell_csr(self) -> Csr:
+        """Rows of ``cell_csr`` that belong to support cells (all of them unless the graph carries test cells): the
+        transpose of ``gene_csr``, used by the backward of the gene aggregation.  Keeps the dense block."""
+        cs, ns = self.cell_csr, self.num_support
+        if ns == self.num_cells:
+            return cs
+        cached = getattr(self, "_support_csr", None)
+        if cached is None or cached[0] is not cs:
+            e = int(cs.rowptr[ns])
+            deg = cs.rowptr[1:ns + 1] - cs.rowptr[:ns]
+            sub = Csr(cs.rowptr[:ns + 1].contiguous(), cs.col[:e], cs.x[:e], cs.n_src, ns, cs.col_bits,
+                      _balanced_row_perm(deg), cs.dense, cs.dense_side)
+            cached = self._support_csr = (cs, sub)
+        return cached[1]
 
     def transpose_of_cell_csr(self) -> Csr:
         if self.cell_csr_t is not None:

@@ -104,14 +104,19 @@ def block_aggregate(h, alpha, block: Block, src_id, dst_id, gene_num: int):
 
 @dataclass
 class DenseBlock:
-    """Entries of the popular genes, taken out of a ``Csr`` and stored zero-filled and tile-blocked
-    (``x[tile][k][T]``, T = ``wsage_dense_tile()``; see include/wsage.h and csrc/agg_dense.cuh)."""
-    x: torch.Tensor                              # fp32 [n_tiles * k * T]
-    k: int                                       # sources of the block
-    t: int                                       # destination slots of the block
-    src_ids: Optional[torch.Tensor] = None       # int32 [k] rows of hs (None: source k = row k)
-    dst_map: Optional[torch.Tensor] = None       # int32 [n_dst] destination row -> slot, -1 = not in the block
-    nnz: int = 0                                 # expression entries the block stands for
+    """Entries of the popular genes, taken out of the CSRs and stored ONCE, zero-filled, as 16-bit planes
+    ``plane[cell // 128][slot // 32][cell % 128][slot % 32]`` (include/wsage.h, csrc/dense16.cuh); both
+    directions of the bipartite pass read the same planes through wsage_dense16."""
+    hi: torch.Tensor                             # int16 storage: fp16 (hi part of x * x_scale) or bf16 bits
+    lo: Optional[torch.Tensor]                   # fp16 residual; None for bf16
+    fmt: int                                     # _lib.D16_F16X2 | _lib.D16_BF16
+    cells: int                                   # cells the planes cover
+    gene_slots: int                              # dense genes
+    slots_pad: int
+    gene_ids: torch.Tensor                       # int32 [gene_slots] slot -> gene id
+    slot_of_gene: torch.Tensor                   # int32 [num_genes] gene id -> slot, -1 = not in the block
+    x_scale: float
+    nnz: int = 0                                 # expression entries the block stands for (over all its cells)
 
 
 @dataclass
@@ -124,23 +129,115 @@ class Csr:
     n_dst: int
     col_bits: int = _lib.COL_I32
     row_perm: Optional[torch.Tensor] = None   # int32 [n_dst] warp-assignment order (load balance)
-    dense: Optional[DenseBlock] = None        # entries removed from col/x and handled by the dense-block kernel
+    dense: Optional[DenseBlock] = None        # entries removed from col/x and handled on the tensor cores
+    dense_side: int = 0                       # 0: rows are cells (block sources = genes); 1: rows are genes
 
     @property
     def nnz(self):
         return int(self.x.shape[0])
 
 
+def _timed(record, fn):
+    """Runs fn(); with bench.py's TIMING list set, brackets it with CUDA events on the launching stream."""
+    if TIMING is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    record["events"] = (e0, e1)
+    TIMING.append(record)
+    return r
+
+
+def amax_split16(x, fmt, *, row_ids=None, rowscale=None, transpose=False):
+    """(hi, lo, amax): 16-bit planes of x * rowscale * 2^k for wsage_dense16 (k from the amax, device-side)."""
+    lib = _lib.load()
+    dev = x.device
+    rows = int(row_ids.shape[0]) if row_ids is not None else x.shape[0]
+    cols = x.shape[1]
+    amax = None
+    if fmt == _lib.D16_F16X2:
+        amax = torch.zeros(1, device=dev, dtype=torch.float32)
+        _lib.check(lib.wsage_amax(_ptr(x), x.stride(0), _ptr(row_ids), _ptr(rowscale), rows, cols, _ptr(amax), _stream()), "wsage_amax")
+    if transpose:
+        ld = (rows + 7) // 8 * 8
+        shape = (cols, ld)
+    else:
+        ld = (cols + 7) // 8 * 8
+        shape = (rows, ld)
+    hi = torch.empty(shape, device=dev, dtype=torch.int16)
+    lo = torch.empty(shape, device=dev, dtype=torch.int16) if fmt == _lib.D16_F16X2 else None
+    _lib.check(lib.wsage_split16(_ptr(x), x.stride(0), _ptr(row_ids), _ptr(rowscale), rows, cols, _ptr(amax), fmt,
+                                 1 if transpose else 0, _ptr(hi), _ptr(lo), ld, _stream()), "wsage_split16")
+    return hi, lo, amax, ld
+
+
+def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, dscale=None, selfcoef=None, hself=None,
+            out=None, chunk_rows=0):
+    """The dense block's share of one pass.  side 0: returns out[n_dst, dim] (= dscale·acc + selfcoef·hself);
+    side 1: returns the partial slabs [n_splits, slots_pad, dim] for ``spmm(init=...)``."""
+    lib = _lib.load()
+    dim = hs.shape[1]
+    dev = hs.device
+    a = _lib.Dense16Args()
+    a.x_hi, a.x_lo, a.fmt, a.cells, a.gene_slots, a.x_scale = _ptr(block.hi), _ptr(block.lo), block.fmt, block.cells, block.gene_slots, block.x_scale
+    a.side, a.dim, a.chunk_rows = side, dim, chunk_rows
+    if side == 0:
+        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, transpose=True)
+        a.n_dst = n_dst
+        if out is None:
+            out = torch.empty(n_dst, dim, device=dev, dtype=torch.float32)
+        a.dscale, a.selfcoef = _ptr(dscale), _ptr(selfcoef)
+        if selfcoef is not None:
+            a.hself, a.ld_hself = _ptr(hself), hself.stride(0)
+        a.out, a.ld_out = _ptr(out), out.stride(0)
+    else:
+        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt)
+        a.n_src_cells = n_src_cells
+    a.h_hi, a.h_lo, a.ld_h, a.h_amax = _ptr(h_hi), _ptr(h_lo), ld, _ptr(amax)
+    if side == 1:
+        n_splits = int(lib.wsage_dense16_splits(ctypes.byref(a)))
+        if n_splits <= 0:
+            _lib.check(_lib.EINVAL, "wsage_dense16_splits")
+        out = torch.empty(n_splits, block.slots_pad, dim, device=dev, dtype=torch.float32)
+        a.out, a.ld_out = _ptr(out), dim
+    rec = dict(kind="dense16", side=side, cells=int(n_dst if side == 0 else n_src_cells), gene_slots=block.gene_slots,
+               slots_pad=block.slots_pad, dim=dim, fmt=block.fmt, dense_nnz=block.nnz)
+    _timed(rec, lambda: _lib.check(lib.wsage_dense16(ctypes.byref(a), _stream()), "wsage_dense16"))
+    return out
+
+
 def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want_out=True,
          raw=None, want_raw=False, q=None, want_dot=False, algo=_lib.ALGO_AUTO):
     """acc = Σ_e x_e·hs[col_e];  out = dscale·acc + selfcoef·hself;  raw = acc;  dot = <acc, q>.
 
-    Returns (out, raw, dot) with None for the ones not requested."""
+    Returns (out, raw, dot) with None for the ones not requested.  Entries held by ``csr.dense`` run on the
+    tensor-core kernel first; the CSR walk (or, when the CSR is empty, a plain reduction) adds the rest."""
     _check_mat(hs, "hs", csr.n_src)
     dim = hs.shape[1]
     dev = hs.device
+    if dscale is not None:
+        _check_vec(dscale, "dscale", torch.float32, csr.n_dst)
+    if selfcoef is not None:
+        _check_vec(selfcoef, "selfcoef", torch.float32, csr.n_dst)
+        _check_mat(hself, "hself", csr.n_dst)
     if want_out and out is None:
         out = torch.empty(csr.n_dst, dim, device=dev, dtype=torch.float32)
+    if out is not None:
+        _check_mat(out, "out", csr.n_dst)
+    init = init_map = None
+    if csr.dense is not None:
+        d = csr.dense
+        if csr.dense_side == 0:
+            direct = csr.nnz == 0 and out is not None and raw is None and not want_raw and not want_dot
+            if direct:      # the whole pass is the dense block: its last drain applies the epilogue
+                dense16(d, 0, hs, n_dst=csr.n_dst, dscale=dscale, selfcoef=selfcoef, hself=hself, out=out)
+                return out, None, None
+            init = dense16(d, 0, hs, n_dst=csr.n_dst).unsqueeze(0)
+        else:
+            init = dense16(d, 1, hs, n_src_cells=csr.n_src)
+            init_map = d.slot_of_gene
     if want_raw and raw is None:
         raw = torch.empty(csr.n_dst, dim, device=dev, dtype=torch.float32)
     dot = torch.empty(csr.n_dst, device=dev, dtype=torch.float32) if want_dot else None
@@ -148,14 +245,10 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
     a.rowptr, a.col, a.col_bits, a.x, a.nnz = _ptr(csr.rowptr), _ptr(csr.col), csr.col_bits, _ptr(csr.x), csr.nnz
     a.hs, a.ld_hs, a.n_src, a.n_dst, a.dim = _ptr(hs), hs.stride(0), csr.n_src, csr.n_dst, dim
     if dscale is not None:
-        _check_vec(dscale, "dscale", torch.float32, csr.n_dst)
         a.dscale = _ptr(dscale)
     if selfcoef is not None:
-        _check_vec(selfcoef, "selfcoef", torch.float32, csr.n_dst)
-        _check_mat(hself, "hself", csr.n_dst)
         a.selfcoef, a.hself, a.ld_hself = _ptr(selfcoef), _ptr(hself), hself.stride(0)
     if out is not None:
-        _check_mat(out, "out", csr.n_dst)
         a.out, a.ld_out = _ptr(out), out.stride(0)
     if raw is not None:
         _check_mat(raw, "raw", csr.n_dst)
@@ -166,24 +259,17 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
     if csr.row_perm is not None:
         a.row_perm = _ptr(csr.row_perm)
     a.algo = algo
-    if csr.dense is not None:
-        d = csr.dense
-        a.dense_x, a.dense_k, a.dense_t = _ptr(d.x), d.k, d.t
-        a.dense_src_ids, a.dense_dst_map = _ptr(d.src_ids), _ptr(d.dst_map)
+    if init is not None:
+        a.init, a.init_slabs, a.init_rows, a.init_map = _ptr(init), init.shape[0], init.shape[1], _ptr(init_map)
+        if algo == _lib.ALGO_GATHER:
+            a.algo = _lib.ALGO_AUTO
     lib = _lib.load()
     nbytes = lib.wsage_spmm_workspace_bytes(ctypes.byref(a))
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8) if nbytes else None
     a.workspace, a.workspace_bytes = _ptr(ws), nbytes
-    if TIMING is None:
-        _lib.check(lib.wsage_spmm(ctypes.byref(a), _stream()), "wsage_spmm")
-    else:       # bench.py: per-launch CUDA events on the launching stream
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(lib.wsage_spmm(ctypes.byref(a), _stream()), "wsage_spmm")
-        e1.record()
-        TIMING.append(dict(algo=int(lib.wsage_spmm_algo(ctypes.byref(a))), n_dst=csr.n_dst, n_src=csr.n_src,
-                           nnz=csr.nnz, dim=dim, col_bits=csr.col_bits, self=selfcoef is not None,
-                           dense_nnz=csr.dense.nnz if csr.dense is not None else 0,
-                           dense_pairs=csr.dense.k * csr.dense.t if csr.dense is not None else 0,
-                           n_out=int(out is not None) + int(raw is not None), dot=want_dot, events=(e0, e1)))
+    rec = dict(kind="spmm", n_dst=csr.n_dst, n_src=csr.n_src, nnz=csr.nnz, dim=dim, col_bits=csr.col_bits,
+               self=selfcoef is not None, init=init is not None, n_out=int(out is not None) + int(raw is not None), dot=want_dot)
+    if TIMING is not None:
+        rec["algo"] = int(lib.wsage_spmm_algo(ctypes.byref(a))) if csr.nnz > 0 or init is None else 0
+    _timed(rec, lambda: _lib.check(lib.wsage_spmm(ctypes.byref(a), _stream()), "wsage_spmm"))
     return out, raw, dot

@@ -20,10 +20,9 @@ from typing import List, Tuple
 import torch
 import torch.distributed as dist
 
-from . import ops
-from .gnn import GNN, _CellAggregate
+from .gnn import GNN
 from .graph import BipartiteGraph
-from .ops import Csr
+from .nodeflow import FullGraphFlow
 
 
 def is_dist():
@@ -70,47 +69,14 @@ class AllReduceSum(torch.autograd.Function):
         return g
 
 
-class _GenePartial(torch.autograd.Function):
-    """Shard-local raw gene sums S_g^p = Σ_{c in shard} x_cg·h_c (no α, no normaliser)."""
-
-    @staticmethod
-    def forward(ctx, hc, graph: BipartiteGraph, algo):
-        out, _, _ = ops.spmm(graph.gene_csr, hc, algo=algo)
-        ctx.graph, ctx.algo = graph, algo
-        return out
-
-    @staticmethod
-    def backward(ctx, ds):
-        dhc = None
-        if ctx.needs_input_grad[0]:
-            dhc, _, _ = ops.spmm(ctx.graph.cell_csr, ds.contiguous(), algo=ctx.algo)
-        return dhc, None, None
-
-
 def sharded_forward(model: GNN, graph: BipartiteGraph, features: torch.Tensor, cells_ready=None) -> torch.Tensor:
-    """GNN.forward on this rank's shard: features = cat[gene rows (replicated); local cell rows].
+    """GNN.forward on this rank's shard: features = cat[gene rows (replicated); local cell rows].  The layer loop is
+    the model's own (``GNN._forward_full``); the flow's ``sharded`` flag makes every gene-producing layer all-reduce
+    its raw gene sums and draws the replicated gene rows' dropout mask from a generator seeded alike on every rank.
     ``cells_ready``: event after which the cell rows of ``features`` are valid (see FullGraphFlow)."""
-    g = graph.num_genes
-    a = model.alpha.reshape(-1)
-    h = features
-    ready = cells_ready
-    for i, layer in enumerate(model.layers):
-        if model.dropout:
-            if ready is not None:
-                torch.cuda.current_stream().wait_event(ready)
-                ready = None
-            h = model.dropout(h)
-        hg, hc = h[:g], h[g:]
-        last = i == model.n_layers - 1
-        neigh_c = _CellAggregate.apply(hg, hc, model.alpha, graph, model.spmm_algo, ready)
-        ready = None
-        if last:
-            h = layer(neigh_c)
-        else:
-            s = AllReduceSum.apply(_GenePartial.apply(hc, graph, model.spmm_algo))
-            neigh_g = s * (graph.mean_g * graph.norm_g * a[:g])[:, None] + hg * (graph.mean_g * a[g])[:, None]
-            h = layer(torch.cat([neigh_g, neigh_c], dim=0))
-    return model._classify(h)
+    flow = FullGraphFlow(graph, features, cells_ready=cells_ready)
+    flow.sharded = True
+    return model._forward_full(flow)
 
 
 def allreduce_grads(model: torch.nn.Module):

@@ -40,3 +40,36 @@ def rel_err(a, b):
     a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
     b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def dense_block_matrix(block):
+    """[cells, gene_slots] fp32 values a ``DenseBlock`` stands for: planes
+    ``plane[cell // 128][slot // 32][cell % 128][slot % 32]`` decoded as (hi + lo) / x_scale (include/wsage.h)."""
+    nb = block.slots_pad // 32
+    n_tiles = (block.cells + 127) // 128
+    f16 = block.lo is not None
+    dt = torch.float16 if f16 else torch.bfloat16
+
+    def plane(t):
+        v = t.cpu().view(dt).to(torch.float64).view(n_tiles, nb, 128, 32)
+        return v.permute(0, 2, 1, 3).reshape(n_tiles * 128, nb * 32)[:block.cells, :block.gene_slots]
+
+    m = plane(block.hi)
+    if f16:
+        m = m + plane(block.lo)
+    return (m / block.x_scale).to(torch.float32)
+
+
+def csr_dense_matrix(csr):
+    """[n_dst, n_src] matrix of the entries ``csr.dense`` holds for this CSR (zeros elsewhere)."""
+    d = csr.dense
+    out = torch.zeros(csr.n_dst, csr.n_src)
+    if d is None:
+        return out
+    m = dense_block_matrix(d)
+    ids = d.gene_ids.cpu().to(torch.int64)
+    if csr.dense_side == 0:         # rows = cells, block sources = genes
+        out[:, ids] = m[:csr.n_dst]
+    else:                            # rows = genes, block sources = cells
+        out[ids, :] = m[:csr.n_src].t()
+    return out

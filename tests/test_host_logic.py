@@ -31,6 +31,9 @@ def test_spmm_args_struct_layout_matches_header():
     body = header[header.index("typedef struct wsage_spmm_args {"):header.index("} wsage_spmm_args;")]
     names = re.findall(r"\b([a-z_]+);", body)
     assert names == [f[0] for f in sd._lib.SpmmArgs._fields_]
+    body = header[header.index("typedef struct wsage_dense16_args {"):header.index("} wsage_dense16_args;")]
+    names = re.findall(r"\b([a-z_]+);", body)
+    assert names == [f[0] for f in sd._lib.Dense16Args._fields_]
 
 
 def test_argument_errors_are_reported_not_thrown():
@@ -198,48 +201,54 @@ def test_product_never_imports_the_oracle():
     assert "from oracle" not in gpu_arm and gpu_arm.count("cpu_reference_steps(") == 1
 
 
-def test_densify_splits_expression_matrix_exactly():
-    """BipartiteGraph.densify: CSR remainder + dense block reproduce the expression matrix bit for bit in both
-    directions (host tensors; the kernels that consume the block are covered by tests/test_gpu_dense_block.py)."""
+def _csr_matrix(csr):
     import scipy.sparse as sp
-    from scdeepsort_b200.graph import BipartiteGraph
+    col = csr.col.to(torch.int64)
+    if csr.col_bits == 16:
+        col = col & 0xFFFF
+    return sp.csr_matrix((csr.x.numpy(), col.numpy(), csr.rowptr.numpy()), shape=(csr.n_dst, csr.n_src)).toarray()
+
+
+def test_densify_splits_expression_matrix_exactly():
+    """BipartiteGraph.densify: CSR remainder + the 16-bit block reproduce the expression matrix in both directions
+    (fp16 hi + lo of x·2^k carries 22 bits: ≤ 2^-22 relative; host tensors — the kernel that consumes the block is
+    covered by tests/test_gpu_dense_block.py)."""
+    import scipy.sparse as sp
+    from scds_helpers import csr_dense_matrix
+    from scdeepsort_b200.graph import BipartiteGraph, DeepSortGraph
     rng = np.random.RandomState(0)
     c, g = 300, 150
     pop = np.minimum(1, 3 * np.arange(1, g + 1) ** -0.8)[rng.permutation(g)]
     mask = rng.rand(c, g) < pop[None, :]
     x = sp.csr_matrix(np.where(mask, rng.rand(c, g) + 0.1, 0).astype(np.float32))
     full = x.toarray()
-    tile = sd._lib.load().wsage_dense_tile()
 
-    def rebuild(csr, side):
-        col = csr.col.to(torch.int64)
-        if csr.col_bits == 16:
-            col = col & 0xFFFF
-        a = sp.csr_matrix((csr.x.numpy(), col.numpy(), csr.rowptr.numpy()), shape=(csr.n_dst, csr.n_src)).toarray()
-        d = csr.dense
-        nt = (d.t + tile - 1) // tile
-        xd = d.x.view(nt, d.k, tile).permute(1, 0, 2).reshape(d.k, nt * tile)[:, :d.t].numpy()      # [source, slot]
-        if side == "src":
-            a[:, d.src_ids.numpy()] += xd.T
-        else:
-            slots = d.dst_map.numpy()
-            rows = np.nonzero(slots >= 0)[0]
-            a[rows, :] += xd[:, slots[rows]].T
-        return a
-
-    bg = BipartiteGraph.from_expression(x).densify(0.2, directions=("gene", "cell"))
+    bg = BipartiteGraph.from_expression(x).densify(0.2)
     assert bg.densified and 0 < len(bg.dense_genes) < g
-    assert bg.cell_csr.nnz + bg.cell_csr.dense.nnz == x.nnz == bg.nnz
-    assert np.array_equal(rebuild(bg.cell_csr, "src"), full)
-    assert np.array_equal(rebuild(bg.gene_csr, "dst"), full.T)
-    # columns stay sorted inside every remaining row; the default touches the gene-destination CSR only
+    d = bg.cell_csr.dense
+    assert d is bg.gene_csr.dense and bg.cell_csr.dense_side == 0 and bg.gene_csr.dense_side == 1      # ONE copy, both directions
+    assert d.slots_pad % 128 == 0 and d.hi.numel() == ((c + 127) // 128) * d.slots_pad * 128 == d.lo.numel()
+    assert bg.cell_csr.nnz + d.nnz == x.nnz == bg.nnz and bg.gene_csr.nnz == bg.cell_csr.nnz
+    np.testing.assert_allclose(_csr_matrix(bg.cell_csr) + csr_dense_matrix(bg.cell_csr).numpy(), full, rtol=2.0 ** -21, atol=0)
+    np.testing.assert_allclose(_csr_matrix(bg.gene_csr) + csr_dense_matrix(bg.gene_csr).numpy(), full.T, rtol=2.0 ** -21, atol=0)
+    # the dense genes are gone from the CSRs, the others untouched; columns stay sorted inside every remaining row
+    dense = np.zeros(g, bool); dense[bg.dense_genes.numpy()] = True
+    assert np.array_equal(_csr_matrix(bg.cell_csr)[:, ~dense], full[:, ~dense]) and not _csr_matrix(bg.cell_csr)[:, dense].any()
     rp, col = bg.gene_csr.rowptr.numpy(), (bg.gene_csr.col.to(torch.int64) & 0xFFFF).numpy()
     assert all(np.all(np.diff(col[rp[i]:rp[i + 1]]) > 0) for i in range(g))
-    bg2 = BipartiteGraph.from_expression(x).densify(0.2)
-    assert bg2.cell_csr.dense is None and bg2.gene_csr.dense is not None
+    # bf16 planes: one plane, values rounded to 8 bits
+    bgb = BipartiteGraph.from_expression(x).densify(0.2, fmt="bf16")
+    assert bgb.cell_csr.dense.lo is None and bgb.cell_csr.dense.x_scale == 1.0
+    np.testing.assert_allclose(_csr_matrix(bgb.cell_csr) + csr_dense_matrix(bgb.cell_csr).numpy(), full, rtol=2.0 ** -8, atol=0)
+    # every gene with an edge in the block: the CSRs are empty and wsage_spmm only reduces
+    bga = BipartiteGraph.from_expression(x).densify(0.0)
+    assert bga.cell_csr.nnz == 0 == bga.gene_csr.nnz and bga.nnz == x.nnz
     # nothing popular enough: unchanged
     bg3 = BipartiteGraph.from_expression(x).densify(1.1)
     assert not getattr(bg3, "densified", False) and bg3.gene_csr.dense is None
+    # the mini-batch graph needs the complete CSRs (ADVICE r1): refused after densify
+    with pytest.raises(ValueError, match="complete CSRs"):
+        DeepSortGraph.from_bipartite(bg)
 
 
 def test_bench_reference_arm_prints_exactly_one_json_line():
@@ -264,7 +273,7 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     """Argument checks of the ABI-1001 additions run before any CUDA call, so they are testable here."""
     import ctypes
     lib = sd._lib.load()
-    assert lib.wsage_version() >= 1001 and lib.wsage_dense_tile() % 4 == 0
+    assert lib.wsage_version() >= 1001
     # accumulation chains of the weight gradient are capped at 1024 rows (64 k-blocks of 16)
     assert lib.wsage_grad_w_splits(780_000, 400) == -(-(-(-780_000 // 16)) // 64) == 762
     assert lib.wsage_grad_w_splits(1000, 400) == 1 and lib.wsage_grad_w_splits(0, 400) == 0
@@ -279,22 +288,62 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     a.n_dst, a.n_src, a.dim, a.col_bits, a.nnz = 8, 8, 400, 32, 4
     a.rowptr = a.hs = a.out = one
     a.ld_hs = a.ld_out = 400
-    a.dense_x, a.dense_k, a.dense_t = one, 0, 8
-    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"dense_k" in lib.wsage_last_error()
-    a.dense_k, a.dense_t = 5, 8                     # dense_src_ids == NULL needs dense_k == n_src
-    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"dense_src_ids" in lib.wsage_last_error()
-    a.dense_k, a.algo = 8, 1                        # the gather kernel cannot take a dense block
+    a.init, a.init_slabs, a.init_rows = one, 0, 8
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"init_slabs" in lib.wsage_last_error()
+    a.init_slabs, a.init_rows = 2, 5                # init_map == NULL needs init_rows >= n_dst
+    assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"init_map" in lib.wsage_last_error()
+    a.init_rows, a.algo = 8, 1                      # the gather kernel cannot take seeded accumulators
     assert lib.wsage_spmm(ctypes.byref(a), None) == sd._lib.EINVAL and b"tiled" in lib.wsage_last_error()
     assert lib.wsage_spmm_algo(ctypes.byref(a)) == 0
     a.algo = 0
-    assert lib.wsage_spmm_algo(ctypes.byref(a)) == 2                  # a dense block always takes the tiled kernel
-    assert lib.wsage_spmm_workspace_bytes(ctypes.byref(a)) >= 8 * 400 * 4
+    assert lib.wsage_spmm_algo(ctypes.byref(a)) == 2                  # seeded accumulators always take the tiled kernel
+    a.nnz = 0                                        # empty CSR + init: a plain reduction, no workspace
+    assert lib.wsage_spmm_workspace_bytes(ctypes.byref(a)) == 0
+
+
+def test_dense16_entry_points_validate_arguments_without_a_gpu():
+    """ABI 2000: wsage_amax / wsage_split16 / wsage_dense16 reject bad arguments before any CUDA call."""
+    import ctypes
+    lib = sd._lib.load()
+    assert lib.wsage_version() >= 2000
+    assert lib.wsage_dense16_slots_pad(1) == 128 and lib.wsage_dense16_slots_pad(129) == 256 and lib.wsage_dense16_slots_pad(0) == 0
+    one = ctypes.c_void_p(16)
+    assert lib.wsage_amax(one, 400, None, None, 10, 398, one, None) == sd._lib.EINVAL and b"multiple of 4" in lib.wsage_last_error()
+    assert lib.wsage_amax(one, 400, None, None, 10, 400, None, None) == sd._lib.EINVAL
+    rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, sd._lib.D16_F16X2, 0, one, one, 404, None)
+    assert rc == sd._lib.EINVAL and b"ld_out % 8" in lib.wsage_last_error()
+    rc = lib.wsage_split16(one, 400, one, None, 10, 400, one, sd._lib.D16_F16X2, 0, one, one, 400, None)
+    assert rc == sd._lib.EINVAL and b"row_ids needs transpose" in lib.wsage_last_error()
+    rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, 7, 0, one, one, 400, None)
+    assert rc == sd._lib.EINVAL and b"fmt" in lib.wsage_last_error()
+    a = sd._lib.Dense16Args()
+    a.x_hi = a.x_lo = a.h_hi = a.h_lo = a.out = one
+    a.fmt, a.cells, a.gene_slots, a.x_scale, a.dim, a.ld_h = sd._lib.D16_F16X2, 1000, 200, 1024.0, 400, 400
+    a.side, a.n_src_cells = 1, 1000
+    n = lib.wsage_dense16_splits(ctypes.byref(a))
+    assert n == 1                                   # 1000 cells = one chain of 2048 rows
+    a.cells = a.n_src_cells = 760_000
+    a.gene_slots = 20_000
+    n = lib.wsage_dense16_splits(ctypes.byref(a))
+    assert 2 <= n <= 64                              # (tile, split) items fill the 148 SMs in whole rounds
+    a.n_src_cells = 760_001
+    assert lib.wsage_dense16_splits(ctypes.byref(a)) == 0 and b"n_src_cells" in lib.wsage_last_error()
+    a.n_src_cells, a.dim = 760_000, 516
+    assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"512" in lib.wsage_last_error()
+    a.dim, a.side, a.n_dst, a.ld_h, a.ld_out = 400, 0, 760_000, 16, 400
+    assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"ld_h < gene_slots" in lib.wsage_last_error()
+    a.ld_h, a.selfcoef = 20_000, one
+    assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"hself" in lib.wsage_last_error()
+    a.selfcoef, a.x_scale = None, 0.0
+    assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"x_scale" in lib.wsage_last_error()
 
 
 def test_densify_with_test_cells_splits_all_three_csrs():
     """Inference graphs carry test cells (gene->cell only, utils/preprocess.py:185-187): gene_csr covers the support
-    cells, cell_csr_t is the transpose of the full cell_csr; densify must split both gene-destination CSRs."""
+    cells, cell_csr_t is the transpose of the full cell_csr; densify strips all three and they share one block
+    that covers every cell (the gene-destination side of gene_csr reads only its first num_support cells)."""
     import scipy.sparse as sp
+    from scds_helpers import csr_dense_matrix
     from scdeepsort_b200.graph import BipartiteGraph
     rng = np.random.RandomState(5)
     cs, ct, g = 120, 30, 90
@@ -302,27 +351,16 @@ def test_densify_with_test_cells_splits_all_three_csrs():
     xs = sp.csr_matrix(np.where(rng.rand(cs, g) < pop[None, :], rng.rand(cs, g) + 0.1, 0).astype(np.float32))
     xt = sp.csr_matrix(np.where(rng.rand(ct, g) < pop[None, :], rng.rand(ct, g) + 0.1, 0).astype(np.float32))
     bg = BipartiteGraph.from_expression(xs, xt).densify(0.25)
-    assert bg.densified and bg.cell_csr.dense is None
-    tile = sd._lib.load().wsage_dense_tile()
-
-    def dense_rows(csr):            # [n_dst, n_src] contribution of the dense block
-        d = csr.dense
-        nt = (d.t + tile - 1) // tile
-        xd = d.x.view(nt, d.k, tile).permute(1, 0, 2).reshape(d.k, nt * tile)[:, :d.t].numpy()
-        out = np.zeros((csr.n_dst, csr.n_src), dtype=np.float32)
-        slots = d.dst_map.numpy()
-        rows = np.nonzero(slots >= 0)[0]
-        out[rows, :] = xd[:, slots[rows]].T
-        return out
-
-    def csr_rows(csr):
-        col = csr.col.to(torch.int64)
-        if csr.col_bits == 16:
-            col = col & 0xFFFF
-        return sp.csr_matrix((csr.x.numpy(), col.numpy(), csr.rowptr.numpy()), shape=(csr.n_dst, csr.n_src)).toarray()
-
+    assert bg.densified and bg.cell_csr.dense is bg.gene_csr.dense is bg.cell_csr_t.dense
+    assert bg.cell_csr.dense.cells == cs + ct
     full = sp.vstack([xs, xt]).toarray()
-    assert np.array_equal(csr_rows(bg.gene_csr) + dense_rows(bg.gene_csr), xs.toarray().T)
-    assert np.array_equal(csr_rows(bg.cell_csr_t) + dense_rows(bg.cell_csr_t), full.T)
-    assert np.array_equal(csr_rows(bg.cell_csr), full)
+    tol = dict(rtol=2.0 ** -21, atol=0)
+    np.testing.assert_allclose(_csr_matrix(bg.gene_csr) + csr_dense_matrix(bg.gene_csr).numpy(), xs.toarray().T, **tol)
+    np.testing.assert_allclose(_csr_matrix(bg.cell_csr_t) + csr_dense_matrix(bg.cell_csr_t).numpy(), full.T, **tol)
+    np.testing.assert_allclose(_csr_matrix(bg.cell_csr) + csr_dense_matrix(bg.cell_csr).numpy(), full, **tol)
     assert bg.transpose_of_cell_csr() is bg.cell_csr_t
+    # the support rows of cell_csr (backward of the gene aggregation) keep the block and a consistent nnz
+    sup = bg.support_cell_csr()
+    assert sup.n_dst == cs and sup.dense is bg.cell_csr.dense and sup.nnz == int(bg.cell_csr.rowptr[cs])
+    np.testing.assert_allclose(_csr_matrix(sup) + csr_dense_matrix(sup).numpy(), xs.toarray(), **tol)
+    assert bg.support_cell_csr() is sup

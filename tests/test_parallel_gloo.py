@@ -27,22 +27,16 @@ def _spmm_cpu(csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
               want_raw=False, q=None, want_dot=False, algo=0):
     seg = torch.repeat_interleave(torch.arange(csr.n_dst), csr.rowptr[1:] - csr.rowptr[:-1])
     acc = torch.zeros(csr.n_dst, hs.shape[1]).index_add_(0, seg, hs[_cols(csr)] * csr.x[:, None])
-    d = getattr(csr, "dense", None)
-    if d is not None:          # wsage_spmm_args.dense_*: acc[v] += sum_k xd[slot(v)/T][k][slot(v)%T] * hs[src(k)]
-        tile = sd._lib.load().wsage_dense_tile()
-        n_tiles = (d.t + tile - 1) // tile
-        xd = d.x.view(n_tiles, d.k, tile).permute(1, 0, 2).reshape(d.k, n_tiles * tile)[:, :d.t]      # [source, slot]
-        src = hs if d.src_ids is None else hs[d.src_ids.to(torch.int64)]
-        part = xd.t() @ src                                                                             # [slot, dim]
-        if d.dst_map is None:
-            acc = acc + part
-        else:
-            rows = torch.nonzero(d.dst_map >= 0).flatten()
-            acc[rows] += part[d.dst_map[rows].to(torch.int64)]
+    if getattr(csr, "dense", None) is not None:      # what wsage_dense16 + wsage_spmm(init=...) add: the block's entries
+        from scds_helpers import csr_dense_matrix
+        acc = acc + csr_dense_matrix(csr) @ hs
     o = acc if dscale is None else acc * dscale[:, None]
     if selfcoef is not None:
         o = o + selfcoef[:, None] * hself
-    return (o if want_out else None), (acc if want_raw else None), ((acc * q).sum(1) if want_dot else None)
+    if out is not None:
+        out.copy_(o)
+        o = out
+    return (o if want_out or out is not None else None), (acc if want_raw else None), ((acc * q).sum(1) if want_dot else None)
 
 
 def _free_port():
@@ -85,7 +79,7 @@ def _worker(rank, world, port, q, densify=None):
         parallel.globalize_gene_normalisers(bg)
         feats = synthetic_features(bg, D0)
         if densify:            # every rank picks ITS OWN popular genes from its local degrees: no coordination needed
-            bg.densify(densify[rank], directions=("gene", "cell") if rank == 0 else ("gene",))
+            bg.densify(densify[rank])
             assert bg.densified and bg.gene_csr.dense is not None
         m = _model()
         parallel.broadcast_params(m)
