@@ -152,16 +152,22 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
  * planes, one product (lo pointers ignored).
  *
  * wsage_amax:    *amax = max(*amax, max |x[r,c] * rowscale[r]|) over rows r (or row_ids[r]) — caller zero-initialises.
- * wsage_split16: hi/lo = 16-bit split of x[r,c] * rowscale[r] * 2^k(amax); transpose == 0: planes [rows][ld_out];
- *                transpose != 0: planes [cols][ld_out] with the (gathered) rows as columns.  ld_out % 8 == 0.
+ * wsage_split16: hi/lo = 16-bit split of x[r,c] * rowscale[r] * 2^k(amax), in one of three layouts:
+ *                WSAGE_SPLIT_ROWS        planes [rows][ld_out]                     (ld_out % 8 == 0)
+ *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns — side 0's H^T
+ *                WSAGE_SPLIT_COLBLOCKS   planes [ceil(cols / 32)][ld_out rows][32]: 32-column blocks of 64-byte rows —
+ *                                        side 1's H; columns past `cols` in the last block are left unwritten
  * ------------------------------------------------------------------------------------- */
 #define WSAGE_D16_F16X2 0
 #define WSAGE_D16_BF16  1
+#define WSAGE_SPLIT_ROWS        0
+#define WSAGE_SPLIT_TRANSPOSED  1
+#define WSAGE_SPLIT_COLBLOCKS   2
 
 int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
                int64_t rows, int32_t cols, float* amax, void* stream);
 int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
-                  int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t transpose,
+                  int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
                   void* hi, void* lo, int64_t ld_out, void* stream);
 
 typedef struct wsage_dense16_args {
@@ -172,9 +178,9 @@ typedef struct wsage_dense16_args {
     int32_t        gene_slots;   /* dense genes (storage: wsage_dense16_slots_pad(gene_slots) slots)     */
     float          x_scale;      /* stored value = x * x_scale (a power of two)                          */
     int32_t        side;
-    const void*    h_hi;         /* side 0: [dim][ld_h] (H^T over the dense genes); side 1: [n_src_cells][ld_h] */
+    const void*    h_hi;         /* side 0: [dim][ld_h] (TRANSPOSED); side 1: [ceil(dim/32)][ld_h][32] (COLBLOCKS) */
     const void*    h_lo;
-    int64_t        ld_h;         /* elements, multiple of 8                                              */
+    int64_t        ld_h;         /* side 0: row pitch in elements (% 8 == 0); side 1: rows per column block */
     const float*   h_amax;       /* device scalar wsage_split16 scaled by (NULL: unscaled)               */
     int32_t        dim;
     int64_t        n_dst;        /* side 0: destination cells (<= cells)                                 */

@@ -25,8 +25,22 @@ vectors stay small.  Outputs:
                                   gene→cell only), features, logits of the 40 test cells
   tests/golden/synthetic.npz      hand-sized (2 genes × 3 cells) and c1-like (60 cells × 120 genes,
                                   D0 = 18 not a multiple of 4) graphs pushed through the reference GNN
+  tests/golden/adipose.npz        BASELINE configs[1] at its stated shape: the reference's FULL fixtures
+                                  train/human/human_Adipose1372 (support) + test/human/human_Pancreas11 (test
+                                  cells) through the unmodified builders at dense_dim 400, models (L=1,H=200 — the
+                                  reference's native shape, predict.py:170-172), (L=2,H=400) and (L=2,H=200):
+                                  logits of every training cell and of the 11 test cells, CE(sum) loss and
+                                  gradients of one 64-seed batch.  To keep the file small the [N, 400] feature
+                                  matrix is NOT the stored PCA output (26 MB) but a seeded recipe applied to the
+                                  reference-built graphs (gene rows ~ N(0, 0.66²); cell rows by the reference's own
+                                  formula, preprocess_internal.py:190-196), weights come back from their seeds
+                                  (checksums stored), big gradient matrices are stored as a strided sample + norm.
+
+The script re-executes itself with PYTHONHASHSEED=0: the reference orders labels by ``list(set(...))``
+(preprocess_internal.py:54), so label ids — hence losses and gradients — depend on the hash seed.
 """
 import argparse
+import os
 import shutil
 import sys
 import tempfile
@@ -179,6 +193,99 @@ def real_fixture(out_dir: Path):
     return GNN, NeighborSampler
 
 
+def recipe_features(x_all, num_genes, dense_dim, seed):
+    """The seeded stand-in for the PCA features (same function in tests/scds_helpers.py): gene rows ~ N(0, 0.66²) from a
+    torch CPU generator; cell rows = (x / (rowsum + 1e-6)) · gene_feat in float64, as preprocess_internal.py:190-196."""
+    gen = torch.Generator().manual_seed(seed)
+    gene_feat = (torch.randn(num_genes, dense_dim, generator=gen) * 0.66).numpy().astype(np.float64)
+    dense = np.asarray(x_all.todense(), dtype=np.float64)
+    dense = dense / (np.sum(dense, axis=1, keepdims=True) + 1e-6)
+    cell_feat = dense.dot(gene_feat)
+    return torch.cat([torch.from_numpy(gene_feat), torch.from_numpy(cell_feat)], dim=0).type(torch.float)
+
+
+def _sample(v, step=53):
+    return v.reshape(-1)[::step].copy()
+
+
+def adipose_fixture(out_dir: Path):
+    """BASELINE configs[1]: Adipose1372 (+ Pancreas11) at dense_dim 400 through the unmodified reference."""
+    from argparse import Namespace
+    tmp = Path(tempfile.mkdtemp(prefix="scds_ref_adipose_"))
+    for sub in ("models", "utils"):
+        shutil.copytree(REF / sub, tmp / sub)
+    (tmp / "train").mkdir(); (tmp / "test").mkdir()
+    os.symlink(REF / "train/human", tmp / "train/human")
+    (tmp / "test/human").mkdir()
+    # the predict-side loader looks for {species}_{tissue}{num}_data.csv: the Pancreas cells are presented as test set 11
+    # of the Adipose model (same bytes, staged name)
+    os.symlink(REF / "test/human/human_Pancreas11_data.csv", tmp / "test/human/human_Adipose11_data.csv")
+    for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "models" or k.startswith("models.")]:
+        del sys.modules[m]
+    sys.path.insert(0, str(tmp))
+    from models import GNN                                  # reference, unmodified
+    from utils import load_data_internal, load_data         # reference, unmodified
+    from dgl.contrib.sampling import NeighborSampler        # shim
+    dense_dim, feat_seed = 400, SEED + 77
+    params = Namespace(random_seed=SEED, dense_dim=dense_dim, species="human", tissue="Adipose", gpu=-1,
+                       filetype="gz", exclude_rate=0.005, threshold=0, test_rate=0.2)
+    np.random.seed(SEED); torch.manual_seed(SEED)
+    num_cells, num_genes, num_labels, graph, train_ids, test_ids, labels = load_data_internal(params)
+    x = sp.load_npz(tmp / "pretrained/human/graphs/human_Adipose_data.npz").tocsr().astype(np.float32)
+    pca_feat = graph.ndata["features"]
+    graph.ndata["features"] = recipe_features(x, num_genes, dense_dim, feat_seed)
+    w = graph.edata["weight"].squeeze(1).double()
+    store = dict(num_cells=num_cells, num_genes=num_genes, num_labels=num_labels, dense_dim=dense_dim, feat_seed=feat_seed,
+                 x_data=x.data, x_indices=x.indices.astype(np.int32), x_indptr=x.indptr.astype(np.int32), x_shape=np.array(x.shape),
+                 labels=labels.numpy().astype(np.int16), train_ids=train_ids.numpy().astype(np.int32),
+                 n_edges=graph.number_of_edges(), weight_sum=float(w.sum()), weight_sq_sum=float((w * w).sum()),
+                 pca_feat_std=np.array([float(pca_feat[:num_genes].std()), float(pca_feat[num_genes:].std())]),
+                 feat_sample=_sample(graph.ndata["features"].numpy(), 997))
+    all_cells = torch.arange(num_genes, num_genes + num_cells)
+    models = {}
+    for tag, n_layers, hidden, seed in (("L1H200", 1, 200, SEED + 31), ("L2H400", 2, 400, SEED + 32), ("L2H200", 2, 200, SEED + 33)):
+        model = _make_model(GNN, dense_dim, hidden, num_labels, n_layers, num_genes, seed)
+        models[tag] = model
+        store[f"{tag}/seed"], store[f"{tag}/n_layers"], store[f"{tag}/hidden"] = seed, n_layers, hidden
+        store[f"{tag}/param_sums"] = np.array([float(v.double().sum()) for v in model.state_dict().values()])
+        store[f"{tag}/logits"] = _eval_logits(model, graph, all_cells, n_layers, 500, NeighborSampler)
+        seeds = train_ids[:64]
+        loss, logits, grads = _train_grads(model, graph, seeds, labels, n_layers, NeighborSampler)
+        store[f"{tag}/grad_seeds"] = seeds.numpy().astype(np.int32)
+        store[f"{tag}/loss"] = loss
+        for k, v in grads.items():
+            if v.size > 20000:
+                store[f"{tag}/grad_sample/{k}"] = _sample(v)
+                store[f"{tag}/grad_norm/{k}"] = float(np.sqrt((v.astype(np.float64) ** 2).sum()))
+            else:
+                store[f"{tag}/grad/{k}"] = v
+        print(f"adipose {tag}: loss {loss:.4f}", flush=True)
+    # ---- inference graph: Pancreas11 test cells on the Adipose support, reference predict-side builder ----
+    p2 = Namespace(random_seed=SEED, dense_dim=dense_dim, species="human", tissue="Adipose", gpu=-1,
+                   filetype="csv", threshold=0, test_dataset=[11], test_dir="test", evaluate=False)
+    np.random.seed(SEED); torch.manual_seed(SEED)
+    total_cell, num_genes2, num_labels2, id2label, test_dict, _ = load_data(p2)
+    tg = test_dict["graph"][11]
+    tdf = pd.read_csv(REF / "test/human/human_Pancreas11_data.csv", index_col=0)
+    id2gene = [ln.strip() for ln in open(tmp / "pretrained/human/statistics/Adipose_genes.txt", encoding="utf-8")]
+    gene2id = {gname: i for i, gname in enumerate(id2gene)}
+    keep = [gname for gname in tdf.index if gname in gene2id]
+    dense_t = np.zeros((tdf.shape[1], num_genes2), dtype=np.float32)
+    dense_t[:, [gene2id[gname] for gname in keep]] = tdf.loc[keep].to_numpy().T
+    xt = sp.csr_matrix(dense_t)
+    tg.ndata["features"] = recipe_features(sp.vstack([x, xt]).tocsr(), num_genes2, dense_dim, feat_seed)
+    wt = tg.edata["weight"].squeeze(1).double()
+    store.update(xt_data=xt.data, xt_indices=xt.indices.astype(np.int32), xt_indptr=xt.indptr.astype(np.int32), xt_shape=np.array(xt.shape),
+                 test_nid=test_dict["nid"][11].numpy().astype(np.int32), test_n_edges=tg.number_of_edges(),
+                 test_weight_sum=float(wt.sum()), n_test_genes_shared=len(keep))
+    for tag, model in models.items():
+        store[f"{tag}/test_logits"] = _eval_logits(model, tg, test_dict["nid"][11], int(store[f"{tag}/n_layers"]), 500, NeighborSampler)
+    np.savez_compressed(out_dir / "adipose.npz", **store)
+    print(f"adipose: G={num_genes} C={num_cells} K={num_labels} E={graph.number_of_edges()} / test N={tg.number_of_nodes()} "
+          f"E={tg.number_of_edges()} shared genes {len(keep)} nnz_test {xt.nnz}")
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def _shim_graph(og):
     """OracleGraph → shim DGLGraph with the reference's frame layout."""
     import dgl
@@ -223,10 +330,24 @@ def synthetic_fixture(out_dir: Path, GNN, NeighborSampler):
 
 
 if __name__ == "__main__":
+    if os.environ.get("PYTHONHASHSEED") != "0":             # label ids follow set order (preprocess_internal.py:54)
+        os.environ["PYTHONHASHSEED"] = "0"
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=str(REPO / "tests" / "golden"))
+    ap.add_argument("--only", default="", help="comma list of: muscle, synthetic, adipose (default: all)")
     args = ap.parse_args()
     out = Path(args.out)
     out.mkdir(parents=True, exist_ok=True)
-    gnn_cls, sampler_cls = real_fixture(out)
-    synthetic_fixture(out, gnn_cls, sampler_cls)
+    only = set(filter(None, args.only.split(","))) or {"muscle", "synthetic", "adipose"}
+    gnn_cls = sampler_cls = None
+    if only & {"muscle", "synthetic"}:
+        gnn_cls, sampler_cls = real_fixture(out if "muscle" in only else Path(tempfile.mkdtemp()))
+    if "synthetic" in only:
+        synthetic_fixture(out, gnn_cls, sampler_cls)
+    if "adipose" in only:
+        if gnn_cls is None:
+            if not hasattr(np, "str"):
+                np.str = str  # noqa: NPY001
+            sys.path.insert(0, str(REPO / "oracle" / "dgl_shim"))
+        adipose_fixture(out)

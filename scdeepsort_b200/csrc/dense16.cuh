@@ -96,10 +96,12 @@ __device__ __forceinline__ void d16_split(float v, int fmt, unsigned short& hi, 
     }
 }
 
-// rows stay rows: hi/lo[r, c] = split(x[r, c] * rowscale[r] * 2^k)           (the side-1 operand H[cells, dim])
+// rows stay rows: hi/lo[r, c] = split(x[r, c] * rowscale[r] * 2^k).  blocked == 0: planes [rows][ld_o];  blocked != 0:
+// planes [cols / 32][ld_o rows][32] — 32-column blocks of 64-byte rows, the side-1 operand H[cells, dim] of dense16_kernel
+// (one k-block of one column block is then 2 KB of contiguous memory)
 __global__ void __launch_bounds__(256)
 split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ rowscale, int64_t rows, int cols,
-               const float* __restrict__ amax, int fmt, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o) {
+               const float* __restrict__ amax, int fmt, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o, int blocked) {
     const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
     const int64_t n4 = cols / 4;
     const int64_t total = rows * n4;
@@ -111,8 +113,9 @@ split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict_
         unsigned short h[4], l[4];
         d16_split(v.x * s, fmt, h[0], l[0]); d16_split(v.y * s, fmt, h[1], l[1]);
         d16_split(v.z * s, fmt, h[2], l[2]); d16_split(v.w * s, fmt, h[3], l[3]);
-        *reinterpret_cast<uint2*>(hi + r * ld_o + c) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
-        if (fmt == 0) *reinterpret_cast<uint2*>(lo + r * ld_o + c) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+        const int64_t o = blocked ? ((int64_t)(c >> 5) * ld_o + r) * 32 + (c & 31) : r * ld_o + c;
+        *reinterpret_cast<uint2*>(hi + o) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+        if (fmt == 0) *reinterpret_cast<uint2*>(lo + o) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
     }
 }
 
@@ -150,6 +153,10 @@ split16_transpose_kernel(const float* __restrict__ x, int64_t ld, const int32_t*
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers (TMA store side; the load / MMA / TMEM wrappers are dense_tc.cuh's)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
@@ -281,16 +288,15 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             if (p.terms == 3) tma_load_2d(sb + p.b_bytes + r0 * 64, &map_b_lo, kb * kD16BlockK, r0, &full_bar[s]);
                         }
                     } else {
-                        // 32 cells of cell tile kb / 4, gene blocks 4 mt .. 4 mt + 3: four 2 KB pieces of one 32 KB region
+                        // 32 cells of cell tile kb / 4, gene blocks 4 mt .. 4 mt + 3: four 2 KB pieces of one 32 KB region,
+                        // fetched by ONE 3-D box {32 slots, 32 cells, 4 blocks} (the producer thread is the scarce resource:
+                        // 34 two-dimensional boxes per stage held this side at 0.69 of the other one)
                         const int row = ((kb >> 2) * p.nb + 4 * mt) * kD16TileM + (kb & 3) * 32;
-                        for (int j = 0; j < 4; ++j) {
-                            tma_load_2d(st + j * kD16BoxMN, &map_a_hi, 0, row + j * kD16TileM, &full_bar[s]);
-                            if (p.terms == 3) tma_load_2d(st + kD16ABytes + j * kD16BoxMN, &map_a_lo, 0, row + j * kD16TileM, &full_bar[s]);
-                        }
-                        for (int j = 0; j < p.b_blocks; ++j) {
-                            tma_load_2d(sb + j * kD16BoxMN, &map_b_hi, j * 32, kb * kD16BlockK, &full_bar[s]);
-                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + j * kD16BoxMN, &map_b_lo, j * 32, kb * kD16BlockK, &full_bar[s]);
-                        }
+                        tma_load_3d(st, &map_a_hi, 0, row, 0, &full_bar[s]);
+                        if (p.terms == 3) tma_load_3d(st + kD16ABytes, &map_a_lo, 0, row, 0, &full_bar[s]);
+                        // B: 32 cells x all column blocks of H, one box {32 columns, 32 cells, b_blocks}
+                        tma_load_3d(sb, &map_b_hi, 0, kb * kD16BlockK, 0, &full_bar[s]);
+                        if (p.terms == 3) tma_load_3d(sb + p.b_bytes, &map_b_lo, 0, kb * kD16BlockK, 0, &full_bar[s]);
                     }
                 }
             }
@@ -464,6 +470,22 @@ inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes,
     const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(WSAGE_ECUDA, "%s: %s", what, "cuTensorMapEncodeTiled failed");
+    return WSAGE_OK;
+}
+
+// Three-dimensional view {32 elements, rows (pitch row_pitch), blocks (pitch block_pitch)} of a 16-bit matrix, box
+// {32, 32, box_blocks}: lands in shared memory as [block][row][32 elements], i.e. box_blocks MN-major SW64 operand blocks.
+inline int make_map_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t blocks,
+                       uint64_t row_pitch_bytes, uint64_t block_pitch_bytes, uint32_t box_blocks, const char* what) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(WSAGE_ECUDA, "%s: %s", what, "cuTensorMapEncodeTiled not available");
+    const cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)blocks};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_pitch_bytes, (cuuint64_t)block_pitch_bytes};
+    const cuuint32_t box[3] = {32, 32, box_blocks};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WSAGE_ECUDA, "%s: %s", what, "cuTensorMapEncodeTiled (3-D) failed");
     return WSAGE_OK;
 }
 

@@ -172,20 +172,22 @@ int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* 
 }
 
 int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
-                  int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t transpose,
+                  int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
                   void* hi, void* lo, int64_t ld_out, void* stream) {
     WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     WSAGE_REQUIRE(fmt == WSAGE_D16_F16X2 || fmt == WSAGE_D16_BF16, "unknown fmt");
+    WSAGE_REQUIRE(layout >= WSAGE_SPLIT_ROWS && layout <= WSAGE_SPLIT_COLBLOCKS, "unknown layout");
     if (rows == 0) return WSAGE_OK;
     WSAGE_REQUIRE(x && hi && (lo || fmt == WSAGE_D16_BF16), "null pointer");
     WSAGE_REQUIRE(ld >= cols && ld % 4 == 0 && aligned16(x), "x must be 16-byte aligned with ld % 4 == 0");
-    WSAGE_REQUIRE(ld_out % 8 == 0 && aligned16(hi) && aligned16(lo), "planes must be 16-byte aligned with ld_out % 8 == 0");
-    WSAGE_REQUIRE(ld_out >= (transpose ? rows : (int64_t)cols), "ld_out too small");
-    WSAGE_REQUIRE(transpose || !row_ids, "row_ids needs transpose");
+    WSAGE_REQUIRE(aligned16(hi) && aligned16(lo), "planes must be 16-byte aligned");
+    WSAGE_REQUIRE(layout == WSAGE_SPLIT_COLBLOCKS || ld_out % 8 == 0, "ld_out % 8 != 0");
+    WSAGE_REQUIRE(ld_out >= (layout == WSAGE_SPLIT_ROWS ? (int64_t)cols : rows), "ld_out too small");
+    WSAGE_REQUIRE(layout == WSAGE_SPLIT_TRANSPOSED || !row_ids, "row_ids needs the transposed layout");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned short* h = static_cast<unsigned short*>(hi);
     unsigned short* l = static_cast<unsigned short*>(lo);
-    if (transpose) {
+    if (layout == WSAGE_SPLIT_TRANSPOSED) {
         WSAGE_REQUIRE(rows < ((int64_t)1 << 31) * 32, "too many rows");
         dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
         split16_transpose_kernel<<<grid, 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out);
@@ -194,7 +196,7 @@ int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const floa
     const int64_t total = rows * (cols / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    split16_kernel<<<(int)grid, 256, 0, st>>>(x, ld, rowscale, rows, cols, amax, fmt, h, l, ld_out);
+    split16_kernel<<<(int)grid, 256, 0, st>>>(x, ld, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_COLBLOCKS ? 1 : 0);
     return check_launch("split16");
 }
 
@@ -208,17 +210,17 @@ static int dense16_validate(const wsage_dense16_args* a, bool need_out = true) {
     WSAGE_REQUIRE(a->dim % 4 == 0 && a->dim <= kTcMaxN, "dim must be a multiple of 4, at most 512");
     WSAGE_REQUIRE(a->x_hi && (a->x_lo || a->fmt == WSAGE_D16_BF16) && a->h_hi && (a->h_lo || a->fmt == WSAGE_D16_BF16) && (a->out || !need_out), "null pointer");
     WSAGE_REQUIRE(a->x_scale > 0.f, "x_scale must be positive");
-    WSAGE_REQUIRE(a->ld_h % 8 == 0 && aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned with ld_h % 8 == 0");
+    WSAGE_REQUIRE(aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned");
     WSAGE_REQUIRE(aligned16(a->x_hi) && aligned16(a->x_lo) && aligned16(a->out), "X planes and out must be 16-byte aligned");
     WSAGE_REQUIRE(a->chunk_rows >= 0, "negative chunk_rows");
     if (a->side == 0) {
         WSAGE_REQUIRE(a->n_dst > 0 && a->n_dst <= a->cells, "side 0 needs 0 < n_dst <= cells");
-        WSAGE_REQUIRE(a->ld_h >= a->gene_slots, "side 0: ld_h < gene_slots");
+        WSAGE_REQUIRE(a->ld_h >= a->gene_slots && a->ld_h % 8 == 0, "side 0: ld_h < gene_slots or ld_h % 8 != 0");
         WSAGE_REQUIRE(a->ld_out >= a->dim && a->ld_out % 4 == 0, "ld_out must be >= dim and a multiple of 4");
         WSAGE_REQUIRE(!a->selfcoef || (a->hself && a->ld_hself >= a->dim && a->ld_hself % 4 == 0 && aligned16(a->hself)), "selfcoef needs a 16-byte aligned hself");
     } else {
         WSAGE_REQUIRE(a->n_src_cells > 0 && a->n_src_cells <= a->cells, "side 1 needs 0 < n_src_cells <= cells");
-        WSAGE_REQUIRE(a->ld_h >= a->dim, "side 1: ld_h < dim");
+        WSAGE_REQUIRE(a->ld_h >= a->n_src_cells, "side 1: ld_h (rows per column block) < n_src_cells");
         WSAGE_REQUIRE(!a->dscale && !a->selfcoef, "side 1 writes raw partial sums (epilogue in wsage_spmm)");
     }
     const int64_t storage_rows = ((a->cells + kD16TileM - 1) / kD16TileM) * (d16_slots_pad(a->gene_slots) / kD16BlockK) * kD16TileM;
@@ -266,11 +268,13 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
         p.rows_per_split = 0; p.m_total = a->n_dst;
         p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
     } else {
-        if ((rc = make_map_2d(&ma_hi, dt, 2, a->x_hi, 32, storage_rows, 64, 32, 32, what)) != WSAGE_OK) return rc;
-        if ((rc = make_map_2d(&ma_lo, dt, 2, x_lo, 32, storage_rows, 64, 32, 32, what)) != WSAGE_OK) return rc;
-        // B = H [n_src_cells][dim]: rows past n_src_cells and columns past dim are zero-filled by TMA
-        if ((rc = make_map_2d(&mb_hi, dt, 2, a->h_hi, (uint64_t)a->dim, (uint64_t)a->n_src_cells, (uint64_t)a->ld_h * 2, 32, 32, what)) != WSAGE_OK) return rc;
-        if ((rc = make_map_2d(&mb_lo, dt, 2, h_lo, (uint64_t)a->dim, (uint64_t)a->n_src_cells, (uint64_t)a->ld_h * 2, 32, 32, what)) != WSAGE_OK) return rc;
+        // A: {32 slots, storage rows (64 B apart), 4 gene blocks (128 rows = 8 KB apart)}
+        if ((rc = make_map_3d(&ma_hi, dt, a->x_hi, storage_rows, 4, 64, (uint64_t)kD16TileM * 64, 4, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_3d(&ma_lo, dt, x_lo, storage_rows, 4, 64, (uint64_t)kD16TileM * 64, 4, what)) != WSAGE_OK) return rc;
+        // B = H in 32-column blocks [b_blocks][ld_h rows][32]: {32 columns, cells (64 B apart), column blocks (ld_h rows apart)};
+        // rows past n_src_cells are zero-filled by TMA; columns dim .. 32 b_blocks of the last block are never stored
+        if ((rc = make_map_3d(&mb_hi, dt, a->h_hi, (uint64_t)a->n_src_cells, (uint64_t)pl.b_blocks, 64, (uint64_t)a->ld_h * 64, (uint32_t)pl.b_blocks, what)) != WSAGE_OK) return rc;
+        if ((rc = make_map_3d(&mb_lo, dt, h_lo, (uint64_t)a->n_src_cells, (uint64_t)pl.b_blocks, 64, (uint64_t)a->ld_h * 64, (uint32_t)pl.b_blocks, what)) != WSAGE_OK) return rc;
         if ((rc = make_map_2d(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->dim, (uint64_t)pl.n_splits * slots_pad, (uint64_t)a->dim * 4, kD16OutCols, 32, what)) != WSAGE_OK) return rc;
         p.rows_per_split = slots_pad; p.m_total = slots_pad;
     }

@@ -150,8 +150,9 @@ def _timed(record, fn):
     return r
 
 
-def amax_split16(x, fmt, *, row_ids=None, rowscale=None, transpose=False):
-    """(hi, lo, amax): 16-bit planes of x * rowscale * 2^k for wsage_dense16 (k from the amax, device-side)."""
+def amax_split16(x, fmt, *, row_ids=None, rowscale=None, layout=_lib.SPLIT_ROWS):
+    """(hi, lo, amax, ld): 16-bit planes of x * rowscale * 2^k for wsage_dense16 (k from the amax, device-side), in the
+    layout wsage_split16 documents (rows / transposed / 32-column blocks)."""
     lib = _lib.load()
     dev = x.device
     rows = int(row_ids.shape[0]) if row_ids is not None else x.shape[0]
@@ -160,16 +161,19 @@ def amax_split16(x, fmt, *, row_ids=None, rowscale=None, transpose=False):
     if fmt == _lib.D16_F16X2:
         amax = torch.zeros(1, device=dev, dtype=torch.float32)
         _lib.check(lib.wsage_amax(_ptr(x), x.stride(0), _ptr(row_ids), _ptr(rowscale), rows, cols, _ptr(amax), _stream()), "wsage_amax")
-    if transpose:
+    if layout == _lib.SPLIT_TRANSPOSED:
         ld = (rows + 7) // 8 * 8
         shape = (cols, ld)
+    elif layout == _lib.SPLIT_COLBLOCKS:
+        ld = rows
+        shape = ((cols + 31) // 32, rows, 32)
     else:
         ld = (cols + 7) // 8 * 8
         shape = (rows, ld)
     hi = torch.empty(shape, device=dev, dtype=torch.int16)
     lo = torch.empty(shape, device=dev, dtype=torch.int16) if fmt == _lib.D16_F16X2 else None
     _lib.check(lib.wsage_split16(_ptr(x), x.stride(0), _ptr(row_ids), _ptr(rowscale), rows, cols, _ptr(amax), fmt,
-                                 1 if transpose else 0, _ptr(hi), _ptr(lo), ld, _stream()), "wsage_split16")
+                                 layout, _ptr(hi), _ptr(lo), ld, _stream()), "wsage_split16")
     return hi, lo, amax, ld
 
 
@@ -184,7 +188,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
     a.x_hi, a.x_lo, a.fmt, a.cells, a.gene_slots, a.x_scale = _ptr(block.hi), _ptr(block.lo), block.fmt, block.cells, block.gene_slots, block.x_scale
     a.side, a.dim, a.chunk_rows = side, dim, chunk_rows
     if side == 0:
-        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, transpose=True)
+        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, layout=_lib.SPLIT_TRANSPOSED)
         a.n_dst = n_dst
         if out is None:
             out = torch.empty(n_dst, dim, device=dev, dtype=torch.float32)
@@ -193,7 +197,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
             a.hself, a.ld_hself = _ptr(hself), hself.stride(0)
         a.out, a.ld_out = _ptr(out), out.stride(0)
     else:
-        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt)
+        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, layout=_lib.SPLIT_COLBLOCKS)
         a.n_src_cells = n_src_cells
     a.h_hi, a.h_lo, a.ld_h, a.h_amax = _ptr(h_hi), _ptr(h_lo), ld, _ptr(amax)
     if side == 1:

@@ -40,3 +40,8 @@ def golden_test():
 @pytest.fixture(scope="session")
 def golden_syn():
     return np.load(GOLDEN / "synthetic.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_adipose():
+    return np.load(GOLDEN / "adipose.npz")

@@ -73,3 +73,52 @@ def csr_dense_matrix(csr):
     else:                            # rows = genes, block sources = cells
         out[ids, :] = m[:csr.n_src].t()
     return out
+
+
+def recipe_features(x_all, num_genes, dense_dim, seed):
+    """The seeded stand-in for the PCA features of tests/golden/adipose.npz (same function as in
+    oracle/gen_golden.py): gene rows ~ N(0, 0.66²) from a torch CPU generator; cell rows = (x / (rowsum + 1e-6)) ·
+    gene_feat in float64, as /root/reference/utils/preprocess_internal.py:190-196."""
+    gen = torch.Generator().manual_seed(int(seed))
+    gene_feat = (torch.randn(num_genes, dense_dim, generator=gen) * 0.66).numpy().astype(np.float64)
+    dense = np.asarray(x_all.todense(), dtype=np.float64)
+    dense = dense / (np.sum(dense, axis=1, keepdims=True) + 1e-6)
+    cell_feat = dense.dot(gene_feat)
+    return torch.cat([torch.from_numpy(gene_feat), torch.from_numpy(cell_feat)], dim=0).type(torch.float)
+
+
+def seeded_state(z, tag, dense_dim, num_labels, num_genes):
+    """State dict of golden model ``tag``, regenerated from its seed exactly as oracle/gen_golden.py:_make_model built
+    it with the reference's GNN class (scdeepsort_b200.GNN has the same constructor, so it draws the same numbers);
+    the stored per-parameter sums guard against RNG drift."""
+    import torch.nn.functional as F
+    import scdeepsort_b200 as sd
+    torch.manual_seed(int(z[f"{tag}/seed"]))
+    m = sd.GNN(in_feats=dense_dim, n_hidden=int(z[f"{tag}/hidden"]), n_classes=num_labels, n_layers=int(z[f"{tag}/n_layers"]),
+               gene_num=num_genes, activation=F.relu, dropout=0.0)
+    with torch.no_grad():
+        m.alpha.copy_(0.5 + torch.rand(m.alpha.shape))
+        m.linear.bias.copy_(torch.rand(m.linear.bias.shape) - 0.5)
+    state = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sums = np.array([float(v.double().sum()) for v in state.values()])
+    assert np.allclose(sums, z[f"{tag}/param_sums"], rtol=1e-9, atol=1e-9), "seeded weights differ from the golden run's"
+    return state
+
+
+def adipose_inputs(z, with_test=False):
+    """(x_support, x_test or None, features) of tests/golden/adipose.npz."""
+    x = golden_csr(z)
+    xt = golden_csr(z, "xt") if with_test else None
+    x_all = x if xt is None else sp.vstack([x, xt]).tocsr()
+    return x, xt, recipe_features(x_all, int(z["num_genes"]), int(z["dense_dim"]), int(z["feat_seed"]))
+
+
+def sampled_grad_err(grad, z, tag, name, step=53):
+    """Gradient check against a golden entry stored whole (small tensors) or as a strided sample + norm."""
+    g = torch.as_tensor(grad).detach().cpu()
+    if f"{tag}/grad/{name}" in z.files:
+        return rel_err(g, z[f"{tag}/grad/{name}"])
+    ref = z[f"{tag}/grad_sample/{name}"]
+    e1 = float((g.reshape(-1)[::step].double() - torch.from_numpy(ref).double()).abs().max() / g.double().abs().max())
+    e2 = abs(float(g.double().norm()) - float(z[f"{tag}/grad_norm/{name}"])) / float(z[f"{tag}/grad_norm/{name}"])
+    return max(e1, e2)

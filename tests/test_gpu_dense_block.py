@@ -105,7 +105,7 @@ def test_spmm_dense_block_matches_plain_csr_and_fp64(n_cells, n_genes, dim, thr)
         assert rel_err(r2.cpu(), acc) < 1e-5
         assert rel_err(o2.cpu(), ref_out) < 1e-5
         assert rel_err(d2.cpu(), (acc * q.double().cpu()).sum(1)) < 1e-5
-        assert rel_err(o2.cpu(), o1.cpu()) < 1e-5 and rel_err(r2.cpu(), r1.cpu()) < 1e-5
+        assert rel_err(o2.cpu(), o1.cpu()) < 2e-5 and rel_err(r2.cpu(), r1.cpu()) < 2e-5       # each is within 1e-5 of fp64
         assert torch.equal(o2, sd.spmm(b, hs, **kw)[0])                  # deterministic
         o3 = sd.spmm(b, hs, dscale=dscale, selfcoef=selfcoef, hself=hself)[0]       # side 0 + empty CSR: fused epilogue
         assert rel_err(o3.cpu(), ref_out) < 1e-5
@@ -161,7 +161,8 @@ def test_dense_block_c3_agrees_with_plain_and_checksum():
             o2 = sd.spmm(b, hs[which])[0]
             assert float((o_plain[which] - o2).abs().max() / o_plain[which].abs().max()) < 2e-5
             ones = sd.spmm(b, torch.ones(b.n_src, 400, device=DEV))[0]
-            assert float((ones[:, ::57] - rs[which][:, None]).abs().max() / rs[which].max()) < 1e-5
+            # all-positive sums are the worst case of the tensor core's truncating accumulation (2048-row chains: ≤ ~1.3e-5)
+            assert float((ones[:, ::57] - rs[which][:, None]).abs().max() / rs[which].max()) < 2e-5
         hg = torch.randn(split.num_genes, 400, device=DEV, generator=g)
         yc = torch.randn(split.num_cells, 400, device=DEV, generator=g)
         ah = sd.spmm(split.cell_csr, hg)[0]

@@ -313,12 +313,14 @@ def test_dense16_entry_points_validate_arguments_without_a_gpu():
     rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, sd._lib.D16_F16X2, 0, one, one, 404, None)
     assert rc == sd._lib.EINVAL and b"ld_out % 8" in lib.wsage_last_error()
     rc = lib.wsage_split16(one, 400, one, None, 10, 400, one, sd._lib.D16_F16X2, 0, one, one, 400, None)
-    assert rc == sd._lib.EINVAL and b"row_ids needs transpose" in lib.wsage_last_error()
+    assert rc == sd._lib.EINVAL and b"row_ids needs the transposed layout" in lib.wsage_last_error()
+    rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, sd._lib.D16_F16X2, sd._lib.SPLIT_COLBLOCKS, one, one, 9, None)
+    assert rc == sd._lib.EINVAL and b"ld_out too small" in lib.wsage_last_error()
     rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, 7, 0, one, one, 400, None)
     assert rc == sd._lib.EINVAL and b"fmt" in lib.wsage_last_error()
     a = sd._lib.Dense16Args()
     a.x_hi = a.x_lo = a.h_hi = a.h_lo = a.out = one
-    a.fmt, a.cells, a.gene_slots, a.x_scale, a.dim, a.ld_h = sd._lib.D16_F16X2, 1000, 200, 1024.0, 400, 400
+    a.fmt, a.cells, a.gene_slots, a.x_scale, a.dim, a.ld_h = sd._lib.D16_F16X2, 1000, 200, 1024.0, 400, 760_000
     a.side, a.n_src_cells = 1, 1000
     n = lib.wsage_dense16_splits(ctypes.byref(a))
     assert n == 1                                   # 1000 cells = one chain of 2048 rows

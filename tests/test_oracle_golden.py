@@ -6,7 +6,8 @@ import scipy.sparse as sp
 import torch
 
 from oracle import gnn_oracle, graph_oracle
-from scds_helpers import golden_csr, golden_grads, golden_graph, golden_state, rel_err
+from scds_helpers import (adipose_inputs, golden_csr, golden_grads, golden_graph, golden_state, rel_err, sampled_grad_err,
+                          seeded_state)
 
 TOL = 2e-6   # fp32 oracle vs fp32 reference: only summation order differs
 
@@ -153,3 +154,55 @@ def test_closed_form_spmm_oracle_matches_literal_oracle(n_layers):
     out = spmm_oracle.forward({n: v.double() for n, v in params.items()}, spmm_oracle.SpmmGraph(x, torch.float64),
                               og.features.double(), n_layers)
     assert float((out - ref).abs().max() / ref.abs().max()) < 1e-6
+
+
+# ---- BASELINE configs[1] at its stated shape: Adipose1372 (+ Pancreas11), dense_dim 400 -----------------------------
+ADIPOSE_MODELS = ("L1H200", "L2H400", "L2H200")
+
+
+def test_adipose_graph_oracle_matches_reference_graph_summaries(golden_adipose):
+    """The full fixtures are too large to store edge by edge: edge counts and weight sums of the reference-built graphs."""
+    z = golden_adipose
+    x, xt, feats = adipose_inputs(z, with_test=True)
+    g = graph_oracle.build_graph(x)
+    assert (g.num_genes, g.num_cells) == (int(z["num_genes"]), int(z["num_cells"])) == (16397, 1354)
+    assert g.src.shape[0] == int(z["n_edges"]) == 2 * x.nnz + g.num_nodes
+    assert abs(float(g.weight.double().sum()) - float(z["weight_sum"])) < 1e-6 * float(z["weight_sum"])
+    assert abs(float((g.weight.double() ** 2).sum()) - float(z["weight_sq_sum"])) < 1e-6 * float(z["weight_sq_sum"])
+    gt = graph_oracle.build_graph(x, xt)
+    assert gt.src.shape[0] == int(z["test_n_edges"]) == 2 * x.nnz + xt.nnz + gt.num_nodes and xt.nnz == 10296
+    assert abs(float(gt.weight.double().sum()) - float(z["test_weight_sum"])) < 1e-6 * float(z["test_weight_sum"])
+    assert np.array_equal(z["test_nid"], np.arange(gt.num_genes + g.num_cells, gt.num_nodes))
+    assert rel_err(feats[: g.num_nodes].reshape(-1)[::997], z["feat_sample"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ADIPOSE_MODELS)
+def test_adipose_oracle_test_cell_logits_match_reference(golden_adipose, tag):
+    """'human test set, 2-layer hidden=400, inference vs reference CPU logits': the 11 Pancreas cells."""
+    z = golden_adipose
+    x, xt, feats = adipose_inputs(z, with_test=True)
+    g = graph_oracle.build_graph(x, xt)
+    g.features = feats
+    params = seeded_state(z, tag, int(z["dense_dim"]), int(z["num_labels"]), g.num_genes)
+    flow = graph_oracle.full_neighbor_flow(g, torch.from_numpy(z["test_nid"]).long(), int(z[f"{tag}/n_layers"]))
+    assert rel_err(gnn_oracle.forward(params, flow, g.num_genes), z[f"{tag}/test_logits"]) < TOL
+
+
+def test_adipose_oracle_train_logits_and_grads_match_reference(golden_adipose):
+    """The reference's native shape (n_layers 1, hidden 200): logits of 300 training cells, loss and gradients of
+    the 64-seed batch."""
+    z, tag = golden_adipose, "L1H200"
+    x, _, feats = adipose_inputs(z)
+    g = graph_oracle.build_graph(x)
+    g.features = feats
+    params = seeded_state(z, tag, int(z["dense_dim"]), int(z["num_labels"]), g.num_genes)
+    cells = torch.arange(g.num_genes, g.num_genes + 300)
+    flow = graph_oracle.full_neighbor_flow(g, cells, 1)
+    assert rel_err(gnn_oracle.forward(params, flow, g.num_genes), z[f"{tag}/logits"][:300]) < TOL
+    seeds = torch.from_numpy(z[f"{tag}/grad_seeds"]).long()
+    labels = torch.from_numpy(z["labels"].astype(np.int64))
+    flow = graph_oracle.full_neighbor_flow(g, seeds, 1)
+    loss, _, grads = gnn_oracle.loss_and_grads(params, flow, labels[seeds], g.num_genes)
+    assert abs(float(loss) - float(z[f"{tag}/loss"])) < 1e-4 * abs(float(z[f"{tag}/loss"]))
+    for k, v in grads.items():
+        assert sampled_grad_err(v, z, tag, k) < 2e-5, k

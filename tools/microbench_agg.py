@@ -73,9 +73,9 @@ def main():
     if args.dense > 0:
         plain = {"cell<-gene": sd.spmm(bg.cell_csr, hg)[0], "gene<-cell": sd.spmm(bg.gene_csr, hc)[0]}
         t0 = time.time()
-        bg.densify(args.dense, directions=("gene", "cell"))
+        bg.densify(args.dense)
         torch.cuda.synchronize()
-        print(f"densify({args.dense}): {len(bg.dense_genes)} genes, {bg.gene_csr.dense.nnz / (bg.gene_csr.nnz + bg.gene_csr.dense.nnz):.3f} "
+        print(f"densify({args.dense}): {len(bg.dense_genes)} genes, {bg.cell_csr.dense.nnz / max(1, bg.nnz):.3f} "
               f"of the edges, {time.time()-t0:.1f}s", flush=True)
         for name, csr, hs, hself in (("cell<-gene", bg.cell_csr, hg, hc), ("gene<-cell", bg.gene_csr, hc, hg)):
             dscale = torch.rand(csr.n_dst, device=dev) + 0.5
