@@ -68,11 +68,16 @@ def block_aggregate(h, alpha, block: OracleBlock, src_id, dst_id, gene_num):
 
 
 def forward(params: dict, flow: OracleFlow, gene_num: int, dtype=torch.float32,
-            dropout_masks: Optional[List[torch.Tensor]] = None, activation=F.relu):
+            dropout_masks: Optional[List[torch.Tensor]] = None, activation=F.relu,
+            relu_masks: Optional[List[torch.Tensor]] = None, hidden_out: Optional[list] = None):
     """GNN.forward (gnn.py:58-68).  ``params`` uses the reference's state_dict keys.
 
     dropout_masks[i], if given, is the already-scaled inverted-dropout multiplier applied to
     layer i's node features before aggregation (gnn.py:62-64); None = eval mode.
+    relu_masks[i], if given, replaces layer i's ReLU by a multiplication with that 0/1 mask: gradients are
+    discontinuous where a pre-activation crosses zero, so a gradient comparison between two implementations is only
+    meaningful under the same kink decisions (the tests take the masks from the implementation under test and check
+    separately that they differ from the oracle's own in a negligible share of entries).
     """
     n_layers = len(flow.blocks)
     alpha = params["alpha"].to(dtype)
@@ -84,8 +89,12 @@ def forward(params: dict, flow: OracleFlow, gene_num: int, dtype=torch.float32,
         w = params[f"layers.{i}.fc_neigh.weight"].to(dtype)
         b = params[f"layers.{i}.fc_neigh.bias"].to(dtype)
         h = neigh @ w.t() + b
-        if activation is not None:
+        if relu_masks is not None:
+            h = h * relu_masks[i].to(dtype)
+        elif activation is not None:
             h = activation(h)
+        if hidden_out is not None:
+            hidden_out.append(h.detach())
     return h @ params["linear.weight"].to(dtype).t() + params["linear.bias"].to(dtype)
 
 

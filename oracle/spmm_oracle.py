@@ -41,7 +41,9 @@ class SpmmGraph:
         self.mean_g = torch.from_numpy(1.0 / (deg_g + 1)).to(dtype)[:, None]
 
 
-def forward(params: dict, graph: SpmmGraph, features: torch.Tensor, n_layers: int) -> torch.Tensor:
+def forward(params: dict, graph: SpmmGraph, features: torch.Tensor, n_layers: int, relu_masks=None, hidden_out=None) -> torch.Tensor:
+    """relu_masks[i] (optional, 0/1, shape of layer i's output) replaces that layer's ReLU — see gnn_oracle.forward."""
+    act = (lambda y, i: torch.relu(y)) if relu_masks is None else (lambda y, i: y * relu_masks[i].to(y.dtype))
     g = graph.num_genes
     a = params["alpha"].reshape(-1, 1)
     h = features
@@ -50,8 +52,10 @@ def forward(params: dict, graph: SpmmGraph, features: torch.Tensor, n_layers: in
         neigh_c = graph.mean_c * (torch.sparse.mm(graph.wc, hg * a[:g]) + a[g + 1] * hc)
         w, b = params[f"layers.{i}.fc_neigh.weight"], params[f"layers.{i}.fc_neigh.bias"]
         if i == n_layers - 1:
-            h = torch.relu(neigh_c @ w.t() + b)
+            h = act(neigh_c @ w.t() + b, i)
         else:
             neigh_g = graph.mean_g * (a[:g] * torch.sparse.mm(graph.wg, hc) + a[g] * hg)
-            h = torch.relu(torch.cat([neigh_g, neigh_c], dim=0) @ w.t() + b)
+            h = act(torch.cat([neigh_g, neigh_c], dim=0) @ w.t() + b, i)
+        if hidden_out is not None:
+            hidden_out.append(h.detach())
     return h @ params["linear.weight"].t() + params["linear.bias"]

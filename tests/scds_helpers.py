@@ -122,3 +122,27 @@ def sampled_grad_err(grad, z, tag, name, step=53):
     e1 = float((g.reshape(-1)[::step].double() - torch.from_numpy(ref).double()).abs().max() / g.double().abs().max())
     e2 = abs(float(g.double().norm()) - float(z[f"{tag}/grad_norm/{name}"])) / float(z[f"{tag}/grad_norm/{name}"])
     return max(e1, e2)
+
+
+class ReluMaskCapture:
+    """Records the 0/1 ReLU decisions of every NodeUpdate of a ``scdeepsort_b200.GNN`` during one forward pass.
+
+    Gradients are discontinuous where a pre-activation crosses zero: two correct fp32 implementations whose forward
+    values differ by 1e-6 take different branches for a few entries out of millions, and each such entry moves a weight
+    gradient by a whole term of its sum.  Gradient parity is therefore checked against the fp64 oracle evaluated under
+    the product's own decisions (``relu_masks=``), and ``disagreement`` bounds how many decisions differ from the
+    oracle's own ReLU (they must be a negligible share, all at |pre-activation| ~ rounding error)."""
+
+    def __init__(self, model):
+        self.masks = []
+        self._handles = [layer.register_forward_hook(lambda mod, inp, out: self.masks.append((out > 0).detach().cpu()))
+                         for layer in model.layers]
+
+    def close(self):
+        for h in self._handles:
+            h.remove()
+
+    @staticmethod
+    def disagreement(masks, oracle_hidden):
+        """Largest share of entries, over the layers, where the product's decision differs from ``oracle_hidden[i] > 0``."""
+        return max(float((m != (h > 0)).float().mean()) for m, h in zip(masks, oracle_hidden))

@@ -11,7 +11,8 @@ import torch
 
 import scdeepsort_b200 as sd
 from oracle import gnn_oracle, graph_oracle, spmm_oracle
-from scds_helpers import adipose_inputs, golden_csr, golden_graph, golden_state, rel_err, sampled_grad_err, seeded_state
+from scds_helpers import (ReluMaskCapture, adipose_inputs, golden_csr, golden_graph, golden_state, rel_err, sampled_grad_err,
+                          seeded_state)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -48,14 +49,30 @@ def test_adipose_minibatch_logits_and_grads_match_reference(golden_adipose, tag)
     assert err < TOL and err < 1e-5, err
     model.train()
     seeds = torch.from_numpy(z[f"{tag}/grad_seeds"]).long()
-    labels = torch.from_numpy(z["labels"].astype(np.int64)).to(DEV)
+    labels = torch.from_numpy(z["labels"].astype(np.int64))
     nf = next(iter(sd.NeighborSampler(g, len(seeds), g.number_of_nodes(), n_layers, 'in', seed_nodes=seeds)))
     nf.copy_from_parent()
-    loss = sd.optim.cross_entropy_sum(model(nf), labels[nf.layer_parent_nid(-1)])
+    cap = ReluMaskCapture(model)
+    loss = sd.optim.cross_entropy_sum(model(nf), labels.to(DEV)[nf.layer_parent_nid(-1)])
+    cap.close()
     loss.backward()
-    assert abs(float(loss) - float(z[f"{tag}/loss"])) < 1e-4 * float(z[f"{tag}/loss"])
+    assert abs(float(loss) - float(z[f"{tag}/loss"])) < 1e-5 * float(z[f"{tag}/loss"])
+    # gradients: (a) against the reference's stored ones — flip-tolerant bar, a ReLU decision that differs moves a weight
+    # gradient by a whole term (ReluMaskCapture); (b) against the fp64 oracle under the product's own decisions: 1e-4
     for name, p in model.named_parameters():
-        assert sampled_grad_err(p.grad, z, tag, name) < TOL, name
+        assert sampled_grad_err(p.grad, z, tag, name) < 1e-3, name
+    og = graph_oracle.build_graph(x)
+    og.features = feats
+    flow = graph_oracle.full_neighbor_flow(og, seeds, n_layers)
+    hidden = []
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    gnn_oracle.forward(state, flow, og.num_genes, dtype=torch.float64, hidden_out=hidden)
+    assert ReluMaskCapture.disagreement(cap.masks, hidden) < 1e-4
+    pp = {k: v.clone().double().requires_grad_(True) for k, v in state.items()}
+    ref = gnn_oracle.forward(pp, flow, og.num_genes, dtype=torch.float64, relu_masks=cap.masks)
+    torch.nn.functional.cross_entropy(ref, labels[seeds], reduction="sum").backward()
+    for name, p in model.named_parameters():
+        assert rel_err(p.grad.cpu(), pp[name].grad) < TOL, name
 
 
 @pytest.mark.parametrize("tag", MODELS)
@@ -122,7 +139,8 @@ def test_predict_labels_bit_equal_to_oracle(golden_adipose):
             ref = gnn_oracle.predict_labels(logits, rate)
             got = sd.predict_labels(logits.to(DEV), rate).cpu()
             assert got.dtype == ref.dtype and torch.equal(got, ref), (tuple(logits.shape), rate)
-    assert (gnn_oracle.predict_labels(cases[0], 2.0) >= 0).any() and (gnn_oracle.predict_labels(cases[3], 2.0) < 0).any()
+    both = gnn_oracle.predict_labels(cases[2], 3.5)            # the rule fires for some rows and not for others
+    assert (both >= 0).any() and (both < 0).any()
 
 
 @pytest.mark.parametrize("path", ["nodeflow", "full", "full_dense"])
@@ -216,15 +234,23 @@ def test_c4_shard_composed_step_vs_fp64_closed_form(dense):
     model.load_state_dict(params)
     model.train()
     labels = torch.randint(0, k, (n,), generator=torch.Generator().manual_seed(10086))
+    cap = ReluMaskCapture(model)
     logits = model(sd.FullGraphFlow(bg, feats))
+    cap.close()
     loss = sd.optim.cross_entropy_sum(logits, labels.to(DEV))
     loss.backward()
-    p = {name: v.detach().clone().double().requires_grad_(True) for name, v in params.items()}
-    ref = spmm_oracle.forward(p, spmm_oracle.SpmmGraph(x, torch.float64), feats.cpu().double(), 2)
+    graph = spmm_oracle.SpmmGraph(x, torch.float64)
+    hidden = []
+    ref = spmm_oracle.forward({name: v.double() for name, v in params.items()}, graph, feats.cpu().double(), 2, hidden_out=hidden)
     loss_ref = torch.nn.functional.cross_entropy(ref, labels, reduction="sum")
-    loss_ref.backward()
-    assert rel_err(logits.detach().cpu(), ref.detach()) < 2e-5
+    assert rel_err(logits.detach().cpu(), ref) < 2e-5
     assert abs(float(loss) - float(loss_ref)) < 1e-5 * float(loss_ref)
+    # gradients under the product's own ReLU decisions (see ReluMaskCapture); the decisions themselves differ from the
+    # oracle's in a negligible share of the 10^7 pre-activations
+    assert ReluMaskCapture.disagreement(cap.masks, hidden) < 1e-4
+    p = {name: v.detach().clone().double().requires_grad_(True) for name, v in params.items()}
+    ref_m = spmm_oracle.forward(p, graph, feats.cpu().double(), 2, relu_masks=cap.masks)
+    torch.nn.functional.cross_entropy(ref_m, labels, reduction="sum").backward()
     for name, v in p.items():
         assert rel_err(dict(model.named_parameters())[name].grad.cpu(), v.grad) < TOL, name
 
