@@ -210,6 +210,8 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream);
  * wsage_split_tf32:  hi = rn_tf32(v), lo = rn_tf32(v - hi), stored as fp32, with v = x, or
  *   v = x * (mask_src > 0) when mask_src is given (ReLU backward, models/gnn.py:22); `masked`
  *   (optional) receives v in fp32.  cols % 4 == 0; all row pitches in elements, multiples of 4.
+ * Passing NULL for BOTH lo operands (split: lo == NULL writes hi only) selects a single tf32 product — the
+ * precision of the bf16 configuration (BASELINE configs[2]), not of the fp32 parity path.
  * wsage_linear_tc:   out[M,N] = act(A[M,K] * B[N,K]^T + bias), A/B given as hi/lo pairs with row
  *   pitches ld_a / ld_b, N <= 512 (computed on N rounded up to 16; the extra rows of B are
  *   zero-filled by TMA); relu != 0 applies max(.,0); bias may be NULL.
@@ -251,7 +253,7 @@ int wsage_sample_neighbors(const int64_t* rowptr, const int64_t* nodes, int64_t 
  * wsage_softmax_ce: CrossEntropyLoss(reduction='sum') of /root/reference/train.py:36,82.  One launch
  *   computes per-block loss partials (loss_partial[0..n_partial), summed by the caller in index order:
  *   deterministic) and, if d_logits != NULL, the gradient softmax(logits) - onehot(labels).
- *   labels are int64 class indices in [0, k).
+ *   labels are int64 class indices in [0, k); a label outside that range makes the loss NaN (nothing is read out of bounds).
  * wsage_adam_step: one torch.optim.Adam(lr, betas, eps, weight_decay) update of n parameters
  *   (train.py:34-35,85; L2 decay added to the gradient, bias correction with `step` >= 1).
  * ------------------------------------------------------------------------------------- */

@@ -21,8 +21,8 @@ import pandas as pd
 import scipy.sparse as sp
 import torch
 
+from .features import cell_features, pca_gene_features
 from .graph import BipartiteGraph, DeepSortGraph
-from .ops import spmm
 from .trainer import Runner, Trainer
 
 
@@ -40,13 +40,16 @@ def _read_table(path, file_type):
     return pd.read_csv(path, **kw)
 
 
-def _features(x_all: sp.csr_matrix, gene_feat: np.ndarray, device) -> torch.Tensor:
-    """cat[gene_feat; (X / (rowsum+1e-6)) · gene_feat]  (preprocess_internal.py:194-202), the SpMM on the GPU."""
-    gf = torch.as_tensor(np.ascontiguousarray(gene_feat), dtype=torch.float32, device=device)
-    bg = BipartiteGraph.from_expression(x_all, device=device)
-    rowsum = torch.as_tensor(np.asarray(x_all.sum(axis=1)).ravel(), dtype=torch.float32, device=device)
-    cell_feat, _, _ = spmm(bg.cell_csr, gf, dscale=1.0 / (rowsum + 1e-6))
-    return torch.cat([gf, cell_feat], dim=0)
+def _features(x_support: sp.csr_matrix, x_test, gene_feat, dense_dim, seed, device):
+    """cat[gene_feat; (X / (rowsum+1e-6)) · gene_feat]  (preprocess_internal.py:186-202; preprocess.py:196-208).  Neither
+    the PCA nor the product ever sees a dense [C, G] array: both run as sparse x thin-dense passes of the aggregation
+    kernels (features.py).  ``gene_feat`` None: fit the PCA on the support cells."""
+    bg = BipartiteGraph.from_expression(x_support, x_test, device=device)
+    if gene_feat is None:
+        gf = pca_gene_features(bg, dense_dim, seed=10086 if seed is None else seed)
+    else:
+        gf = torch.as_tensor(np.ascontiguousarray(gene_feat), dtype=torch.float32, device=device)
+    return torch.cat([gf, cell_features(bg, gf)], dim=0), gf
 
 
 class DeepSortClassifier:
@@ -91,17 +94,13 @@ class DeepSortClassifier:
         return sp.vstack(mats).tocsr(), np.asarray(labels, dtype=np.int64), id2gene, id2label
 
     def fit(self, files, save_path=None):
-        from sklearn.decomposition import PCA
         if self.random_seed is not None:
             np.random.seed(self.random_seed)
             torch.manual_seed(self.random_seed)
         x, labels, id2gene, id2label = self._load_training(files)
         num_cells, num_genes = x.shape
-        dense_dim = min(self.dense_dim, num_cells, num_genes)
-        gene_feat = PCA(dense_dim, random_state=self.random_seed).fit_transform(np.asarray(x.todense()).T)
-        if dense_dim < self.dense_dim:                                          # tiny inputs: pad to the requested width
-            gene_feat = np.pad(gene_feat, ((0, 0), (0, self.dense_dim - dense_dim)))
-        feats = _features(x, gene_feat, self.device)
+        feats, gene_feat = _features(x, None, None, self.dense_dim, self.random_seed, self.device)   # tiny inputs: zero-padded
+        gene_feat = gene_feat.cpu().numpy()
         graph = DeepSortGraph.from_expression(x, threshold=self.threshold, features=feats.cpu())
         perm = np.random.permutation(np.arange(num_genes, num_genes + num_cells))
         n_val = int(num_cells * self.validation_fraction)
@@ -113,8 +112,9 @@ class DeepSortClassifier:
                                hidden_dim=self.hidden_dim, n_layers=self.n_layers, dropout=self.dropout, lr=self.lr,
                                weight_decay=self.weight_decay, batch_size=self.batch_size,
                                num_neighbors=self.num_neighbors, device=self.device, save_path=model_file)
-        best = self.trainer.fit(self.n_epochs, verbose=False)
-        self.trainer.save_model()
+        best = self.trainer.fit(self.n_epochs, verbose=False)      # saves the best-on-validation checkpoint (train.py:53-58)
+        if model_file is not None and not model_file.exists():      # n_epochs == 0: nothing was selected, keep the initial weights
+            self.trainer.save_model()
         if save_path is not None:
             _save_artifacts(Path(save_path), self.species, self.tissue, x, gene_feat, id2gene, id2label)
         self._support = (x, gene_feat, id2gene, id2label)
@@ -171,11 +171,8 @@ class DeepSortPredictor:
         xt = sp.lil_matrix((arr.shape[0], len(self.id2gene)))
         xt[:, [gene2id[str(tab.index[i])] for i in known]] = np.where(arr > 0, arr, 0.0)
         xt = xt.tocsr()
-        gene_feat = self.gene_feat
-        if gene_feat is None:                       # reference artefacts: PCA on the support cells only (preprocess.py:196)
-            from sklearn.decomposition import PCA
-            gene_feat = PCA(self.dense_dim, random_state=10086).fit_transform(np.asarray(self.support.todense()).T)
-        feats = _features(sp.vstack([self.support, xt]).tocsr(), gene_feat, self.device)
+        # reference artefacts carry no gene features: PCA on the support cells only (preprocess.py:196)
+        feats, _ = _features(self.support, xt, self.gene_feat, self.dense_dim, 10086, self.device)
         graph = DeepSortGraph.from_expression(self.support, xt, features=feats.cpu())
         g, ns = graph.num_genes, self.support.shape[0]
         nid = torch.arange(g + ns, g + ns + xt.shape[0])

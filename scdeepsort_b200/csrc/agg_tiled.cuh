@@ -36,9 +36,7 @@ namespace wsage {
 
 constexpr int kTiledStages = 4;                // deepest window ring among the compiled shapes
 constexpr int kTiledSmemBudget = 224 * 1024;   // bytes of window ring per CTA (227 KB max per CTA)
-constexpr int kTiledNW = 12;                   // consumer warps per CTA
-constexpr int kTiledR = 4;                     // destination rows per warp
-constexpr int kTiledDefaultCluster = 1;        // CTAs per cluster sharing window loads (WSAGE_TILED_CLUSTER overrides)
+constexpr int kTiledDefaultCluster = 1;        // CTAs per cluster sharing window loads (-DWSAGE_TUNING: WSAGE_TILED_CLUSTER overrides)
 
 struct TiledParams {
     const int64_t* rowptr;
@@ -526,18 +524,25 @@ tiled_reduce_kernel(const TiledParams p) {
 
 // ------------------------------------------ host side ------------------------------------------
 // Kernel shape: consumer warps per CTA, destination rows per warp, depth of the window ring.
-// WSAGE_TILED_VARIANT (env, tuning only) selects among the compiled shapes for dim == 400.
+//   widths 400 / 200 / 64 (BASELINE's configs and the reference's hidden_dim): 15 consumer warps + producer = 16 warps at
+//     128 registers fill the register file exactly, 60 rows per tile (c4 cell<-gene 94.7 -> 87.1 ms against 12 warps,
+//     profiles/r01_summary.md);
+//   every other width (128, run-time width): 11 consumer warps + producer = 12 warps at 168 registers — the 16-warp shape
+//     (128 registers) spills there.
+// -DWSAGE_TUNING additionally compiles the shapes that lost the round-1 sweeps (ring depth 2 / 4, 12 / 14 / 16 warps, no
+// edge mirror, 2-CTA clusters, the fill-only / walk-only diagnostics) and lets WSAGE_TILED_VARIANT / _DIAG / _CLUSTER pick them
+// for dim == 400.
 struct TiledVariant { int nw, r, stages; bool esm; };
+constexpr TiledVariant kTiledWide = {15, 4, 3, true};
+constexpr TiledVariant kTiledSafe = {11, 4, 3, true};      // 11 + producer = 12 warps: 3 per scheduler, 168 registers
+inline bool tiled_wide_dim(int dim) { return dim == 400 || dim == 200 || dim == 64; }
+
+#ifdef WSAGE_TUNING
 inline int tiled_diag_env() { const char* e = getenv("WSAGE_TILED_DIAG"); const int i = e ? atoi(e) : 0; return (i == 1 || i == 2) ? i : 0; }
 inline int tiled_cluster_env() { const char* e = getenv("WSAGE_TILED_CLUSTER"); return (e && atoi(e) == 2) ? 2 : 1; }
-// [0] = shape of every width but 400 and of the diagnostic / cluster variants; [kTiledDefault400] = default for
-// dim == 400: 15 consumer warps + producer = 16 warps at 128 registers fill the register file exactly, 60 rows
-// per tile instead of 48 (20 % less window-fill traffic, 25 % more warps to hide shared-memory latency):
-// c4 cell<-gene 94.7 -> 87.1 ms, gene<-cell 115.2 -> 106.5 ms (profiles/r01_summary.md)
 constexpr int kTiledDefault400 = 6;
 constexpr TiledVariant kTiledVariants[] = {{12, 4, 3, true}, {12, 4, 3, false}, {12, 4, 4, true}, {16, 3, 4, true}, {12, 4, 2, true}, {14, 4, 3, true}, {15, 4, 3, true}, {15, 4, 4, true}, {15, 4, 2, true}};
 constexpr int kNumTiledVariants = sizeof(kTiledVariants) / sizeof(kTiledVariants[0]);
-
 inline int tiled_variant_index() {
     static const int v = [] {
         const char* e = getenv("WSAGE_TILED_VARIANT");
@@ -547,8 +552,13 @@ inline int tiled_variant_index() {
     }();
     return v;
 }
+#endif
+
 inline TiledVariant tiled_variant(const wsage_spmm_args* a) {
-    return kTiledVariants[a->dim == 400 ? tiled_variant_index() : kTiledDefault400];     // other widths: the default shape
+#ifdef WSAGE_TUNING
+    if (a->dim == 400) return kTiledVariants[tiled_variant_index()];
+#endif
+    return tiled_wide_dim(a->dim) ? kTiledWide : kTiledSafe;
 }
 
 struct TiledPlan {
@@ -617,18 +627,19 @@ inline bool tiled_profitable(const wsage_spmm_args* a, bool vec4) {
 
 struct TiledInit { const float* init; int slabs; int64_t rows; const int32_t* map; };
 
-// Profiling aid (WSAGE_TILED_DIAG, dim 400 default shape only; compile-time variants so that the production kernel
-// carries no extra branch — a run-time flag in the window loop cost 3.7 % of the step): 1 = the producer copies
-// nothing (edge-walk time only, results meaningless), 2 = the consumers skip the edge walk (window-fill time only).
+#ifdef WSAGE_TUNING
+// Profiling aid (WSAGE_TILED_DIAG, dim 400 shape [0] only; compile-time variants so that the production kernel carries no
+// extra branch — a run-time flag in the window loop cost 3.7 % of the step): 1 = the producer copies nothing (edge-walk
+// time only, results meaningless), 2 = the consumers skip the edge walk (window-fill time only).
 inline int tiled_diag() {
     static const int v = tiled_diag_env();
     return v;
 }
-
 inline int tiled_cluster() {      // WSAGE_TILED_CLUSTER = 1 | 2 (dim 400, shape [0] only)
     static const int v = kTiledDefaultCluster == 2 ? 2 : tiled_cluster_env();
     return v;
 }
+#endif
 
 template <typename ColT, int DIM, int NW, int R, int STG, bool ESM, int CL = 1, int DIAG = 0>
 int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const TiledInit& ini, cudaStream_t st) {
@@ -677,26 +688,30 @@ int launch_tiled_shape(const wsage_spmm_args* a, const TiledPlan& pl, const Tile
 
 template <typename ColT>
 int launch_tiled_col(const wsage_spmm_args* a, const TiledPlan& pl, const TiledInit& ini, cudaStream_t st) {
-    switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and the bench (400/400)
+    switch (a->dim) {       // widths of the reference (dense_dim 400, hidden 200) and of BASELINE's configs (400 / 400, 64)
         case 400:
+#ifdef WSAGE_TUNING
             switch (tiled_variant_index()) {
                 case 1: return launch_tiled_shape<ColT, 400, 12, 4, 3, false>(a, pl, ini, st);
                 case 2: return launch_tiled_shape<ColT, 400, 12, 4, 4, true>(a, pl, ini, st);
                 case 3: return launch_tiled_shape<ColT, 400, 16, 3, 4, true>(a, pl, ini, st);
                 case 4: return launch_tiled_shape<ColT, 400, 12, 4, 2, true>(a, pl, ini, st);
                 case 5: return launch_tiled_shape<ColT, 400, 14, 4, 3, true>(a, pl, ini, st);
-                case 6: return launch_tiled_shape<ColT, 400, 15, 4, 3, true>(a, pl, ini, st);
-                case 7: return launch_tiled_shape<ColT, 400, 15, 4, 4, true>(a, pl, ini, st);      // not yet measured
-                case 8: return launch_tiled_shape<ColT, 400, 15, 4, 2, true>(a, pl, ini, st);      // not yet measured
+                case 6: break;
+                case 7: return launch_tiled_shape<ColT, 400, 15, 4, 4, true>(a, pl, ini, st);
+                case 8: return launch_tiled_shape<ColT, 400, 15, 4, 2, true>(a, pl, ini, st);
                 default:
                     if (tiled_diag() == 1) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 1>(a, pl, ini, st);
                     if (tiled_diag() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 1, 2>(a, pl, ini, st);
                     if (tiled_cluster() == 2) return launch_tiled_shape<ColT, 400, 12, 4, 3, true, 2>(a, pl, ini, st);
                     return launch_tiled_shape<ColT, 400, 12, 4, 3, true>(a, pl, ini, st);
             }
+#endif
+            return launch_tiled_shape<ColT, 400, 15, 4, 3, true>(a, pl, ini, st);
         case 200: return launch_tiled_shape<ColT, 200, 15, 4, 3, true>(a, pl, ini, st);
-        case 128: return launch_tiled_shape<ColT, 128, 15, 4, 3, true>(a, pl, ini, st);
-        default:  return launch_tiled_shape<ColT, 0, 15, 4, 3, true>(a, pl, ini, st);
+        case 64:  return launch_tiled_shape<ColT, 64, 15, 4, 3, true>(a, pl, ini, st);
+        case 128: return launch_tiled_shape<ColT, 128, 11, 4, 3, true>(a, pl, ini, st);
+        default:  return launch_tiled_shape<ColT, 0, 11, 4, 3, true>(a, pl, ini, st);
     }
 }
 

@@ -59,7 +59,7 @@ split_tf32_kernel(const float* __restrict__ x, int64_t ld_x, const float* __rest
         h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
         l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y); l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
         *reinterpret_cast<float4*>(hi + r * ld_o + c) = h;
-        *reinterpret_cast<float4*>(lo + r * ld_o + c) = l;
+        if (lo) *reinterpret_cast<float4*>(lo + r * ld_o + c) = l;
     }
 }
 
@@ -114,6 +114,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 struct LinearTcParams {
+    int terms;               // 3: hi*hi + lo*hi + hi*lo (fp32-grade); 1: hi*hi only (plain tf32, the bf16 configuration)
     int64_t m;
     int n, n_pad, k;         // n_pad = N rounded up to 16 (MMA granularity); columns >= N are never stored
     int n1, n2;              // MMA N halves: n1 = min(N, 256), n2 = N - n1 (multiples of 16)
@@ -183,15 +184,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     const uint32_t ph = (it / kTcStages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = ring + (size_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.terms == 3 ? stage_bytes : stage_bytes / 2));
                     const int k0 = kb * kTcBlockK;
                     tma_load_2d(st, &map_a_hi, k0, m0, &full_bar[s]);
-                    tma_load_2d(st + LinearTcSmem::a_bytes, &map_a_lo, k0, m0, &full_bar[s]);
+                    if (p.terms == 3) tma_load_2d(st + LinearTcSmem::a_bytes, &map_a_lo, k0, m0, &full_bar[s]);
                     unsigned char* sb = st + 2 * LinearTcSmem::a_bytes;
                     for (int j = 0; j < p.b_boxes; ++j) {
                         const int r0 = j * p.b_box_rows;
                         tma_load_2d(sb + r0 * kTcBlockK * 4, &map_b_hi, k0, r0, &full_bar[s]);
-                        tma_load_2d(sb + b_bytes + r0 * kTcBlockK * 4, &map_b_lo, k0, r0, &full_bar[s]);
+                        if (p.terms == 3) tma_load_2d(sb + b_bytes + r0 * kTcBlockK * 4, &map_b_lo, k0, r0, &full_bar[s]);
                     }
                 }
             }
@@ -221,12 +222,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                         const uint32_t acc0 = (kb | kk) != 0;
                         // hi*hi, lo*hi, hi*lo  (smallest terms last does not matter: fp32 accumulate)
                         tc_mma_tf32(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
-                        tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
-                        tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                        if (p.terms == 3) {
+                            tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
+                            tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                        }
                         if (p.n2 > 0) {
                             tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
-                            tc_mma_tf32(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
-                            tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                            if (p.terms == 3) {
+                                tc_mma_tf32(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
+                                tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                            }
                         }
                     }
                     tc_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
@@ -332,6 +337,7 @@ constexpr int kGwStages = 3;
 constexpr int kGwABlocks = kTcBlockM / kGwMnBlock;          // 4 MN blocks cover the 128-row M tile
 
 struct GradWParams {
+    int terms;               // 3 | 1, as LinearTcParams
     int64_t rows;            // K extent
     int n_out, n_in;
     int n_pad;               // n_in rounded up to 16
@@ -412,16 +418,16 @@ grad_w_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_cons
                 const uint32_t ph = (it / kGwStages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 unsigned char* st = ring + (size_t)s * stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.terms == 3 ? stage_bytes : stage_bytes / 2));
                 const int k0 = kb * kGwBlockK;
                 for (int j = 0; j < kGwABlocks; ++j) {       // blocks past n_out are zero-filled by TMA
                     tma_load_2d(st + j * kGwBoxBytes, &map_g_hi, m0 + j * kGwMnBlock, k0, &full_bar[s]);
-                    tma_load_2d(st + a_bytes + j * kGwBoxBytes, &map_g_lo, m0 + j * kGwMnBlock, k0, &full_bar[s]);
+                    if (p.terms == 3) tma_load_2d(st + a_bytes + j * kGwBoxBytes, &map_g_lo, m0 + j * kGwMnBlock, k0, &full_bar[s]);
                 }
                 unsigned char* sb = st + 2 * a_bytes;
                 for (int j = 0; j < p.b_blocks; ++j) {
                     tma_load_2d(sb + j * kGwBoxBytes, &map_x_hi, j * kGwMnBlock, k0, &full_bar[s]);
-                    tma_load_2d(sb + b_bytes + j * kGwBoxBytes, &map_x_lo, j * kGwMnBlock, k0, &full_bar[s]);
+                    if (p.terms == 3) tma_load_2d(sb + b_bytes + j * kGwBoxBytes, &map_x_lo, j * kGwMnBlock, k0, &full_bar[s]);
                 }
             }
         }
@@ -444,12 +450,16 @@ grad_w_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_cons
                     const uint64_t ko = (uint64_t)((kk * 1024) >> 4);
                     const uint32_t acc0 = (it | kk) != 0;
                     tc_mma_tf32(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
-                    tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
-                    tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                    if (p.terms == 3) {
+                        tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
+                        tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
+                    }
                     if (p.n2 > 0) {
                         tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
-                        tc_mma_tf32(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
-                        tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                        if (p.terms == 3) {
+                            tc_mma_tf32(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
+                            tc_mma_tf32(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                        }
                     }
                 }
                 tc_commit(&empty_bar[s]);

@@ -29,7 +29,8 @@ softmax_ce_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* _
         sum = warp_sum(sum);
         const int64_t y = labels[r];
         const float lse = mx + logf(sum);
-        if (lane == 0) my_loss += lse - row[y];
+        // a label outside [0, k) (e.g. the -1 of a gene row) must not read out of bounds: it poisons the loss instead
+        if (lane == 0) my_loss += (y >= 0 && y < k) ? lse - row[y] : NAN;
         if (dlogits) {
             const float inv = 1.f / sum;
             for (int c = lane; c < k; c += 32)

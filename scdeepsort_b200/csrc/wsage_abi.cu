@@ -291,7 +291,7 @@ int wsage_split_tf32(const float* x, int64_t ld_x, const float* mask_src, int64_
                      int64_t rows, int32_t cols, void* stream) {
     WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     if (rows == 0) return WSAGE_OK;
-    WSAGE_REQUIRE(x && hi && lo, "null x/hi/lo");
+    WSAGE_REQUIRE(x && hi, "null x/hi");
     WSAGE_REQUIRE(ld_x >= cols && ld_out >= cols && ld_x % 4 == 0 && ld_out % 4 == 0, "bad leading dimension");
     WSAGE_REQUIRE(!mask_src || (ld_mask >= cols && ld_mask % 4 == 0), "bad mask leading dimension");
     WSAGE_REQUIRE(!masked || (mask_src && ld_masked >= cols && ld_masked % 4 == 0), "masked output needs mask_src");
@@ -310,7 +310,10 @@ int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
                     int64_t m, int32_t n, int32_t k, void* stream) {
     WSAGE_REQUIRE(m >= 0 && n > 0 && k > 0, "bad shape");
     if (m == 0) return WSAGE_OK;
-    WSAGE_REQUIRE(a_hi && a_lo && b_hi && b_lo && out, "null pointer");
+    WSAGE_REQUIRE(a_hi && b_hi && out, "null pointer");
+    WSAGE_REQUIRE((a_lo != nullptr) == (b_lo != nullptr), "a_lo and b_lo go together (both NULL: single tf32 product)");
+    const int terms = a_lo ? 3 : 1;
+    if (!a_lo) { a_lo = a_hi; b_lo = b_hi; }             // descriptors only: never loaded when terms == 1
     // the MMA computes n_pad = N rounded up to 16 columns; rows of B past N are zero-filled by TMA
     const int n_pad = (n + 15) & ~15;
     WSAGE_REQUIRE(n_pad <= kTcMaxN, "N must be <= 512");
@@ -318,6 +321,7 @@ int wsage_linear_tc(const float* a_hi, const float* a_lo, int64_t ld_a,
     WSAGE_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo), "operands must be 16-byte aligned");
     WSAGE_REQUIRE(m < ((int64_t)1 << 31) - kTcBlockM, "M too large");
     LinearTcParams p{};
+    p.terms = terms;
     p.m = m; p.n = n; p.n_pad = n_pad; p.k = k;
     p.n1 = n_pad < 256 ? n_pad : 256;
     p.n2 = n_pad - p.n1;
@@ -354,7 +358,10 @@ int wsage_grad_w_tc(const float* g_hi, const float* g_lo, int64_t ld_g,
                     int64_t rows, int32_t n_out, int32_t n_in,
                     float* partial, int32_t n_splits, float* out, int64_t ld_out, void* stream) {
     WSAGE_REQUIRE(rows > 0 && n_out > 0 && n_in > 0, "bad shape");
-    WSAGE_REQUIRE(g_hi && g_lo && x_hi && x_lo && partial && out, "null pointer");
+    WSAGE_REQUIRE(g_hi && x_hi && partial && out, "null pointer");
+    WSAGE_REQUIRE((g_lo != nullptr) == (x_lo != nullptr), "g_lo and x_lo go together (both NULL: single tf32 product)");
+    const int terms = g_lo ? 3 : 1;
+    if (!g_lo) { g_lo = g_hi; x_lo = x_hi; }
     WSAGE_REQUIRE(n_out % 4 == 0 && n_in % 4 == 0, "n_out and n_in must be multiples of 4");
     const int n_pad = (n_in + 15) & ~15;
     WSAGE_REQUIRE(n_pad <= kTcMaxN, "n_in must be <= 512");
@@ -363,6 +370,7 @@ int wsage_grad_w_tc(const float* g_hi, const float* g_lo, int64_t ld_g,
     WSAGE_REQUIRE(rows < ((int64_t)1 << 31) - kGwBlockK, "too many rows");
     WSAGE_REQUIRE(n_splits == wsage_grad_w_splits(rows, n_out), "n_splits must come from wsage_grad_w_splits");
     GradWParams p{};
+    p.terms = terms;
     p.rows = rows; p.n_out = n_out; p.n_in = n_in; p.n_pad = n_pad;
     p.n1 = n_pad < 256 ? n_pad : 256;
     p.n2 = n_pad - p.n1;

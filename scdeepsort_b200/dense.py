@@ -1,11 +1,12 @@
-"""Tensor-core dense layer: PyTorch-facing wrappers of ``wsage_split_tf32`` / ``wsage_linear_tc``.
+"""Tensor-core dense layer: PyTorch-facing wrappers of ``wsage_split_tf32`` / ``wsage_linear_tc`` / ``wsage_grad_w_tc``.
 
 ``linear_relu(x, weight, bias, relu)`` computes ``act(x @ weight.T + bias)`` (NodeUpdate,
 /root/reference/models/gnn.py:18-25) with the tcgen05 kernel: operands split into tf32 hi+lo,
-three MMAs per k-step accumulated in fp32 (error ~5e-7 relative, fp32-grade, far inside the 1e-4 parity bar).
+three MMAs per k-step accumulated in fp32 (error ~3e-6 relative: fp32-grade, far inside the 1e-4 parity bar).
 Backward: the input gradient goes through the same kernel (B = weight transposed), the ReLU mask is
-fused into the split kernel; the weight gradient (a [N, K] reduction over all rows) and the bias
-gradient use torch (cuBLAS fp32) in this round.
+fused into the split kernel, the weight gradient (a [N, K] reduction over all rows) runs on ``wsage_grad_w_tc``;
+only the bias gradient (a column sum) is left to torch.  ``single_product = True`` (set by the bf16 configuration)
+drops the lo operands: one tf32 product per k-step.
 """
 import ctypes
 
@@ -15,13 +16,17 @@ from . import _lib
 from .ops import _ptr, _stream
 
 
+single_product = False     # True: plain tf32 (hi operands only) — BASELINE configs[2], not the fp32 parity path
+
+
 def split_tf32(x: torch.Tensor, mask_src: torch.Tensor = None, want_masked=False):
-    """(hi, lo, masked): hi = rn_tf32(v), lo = rn_tf32(v - hi) as fp32 [rows, cols]; v = x or x * (mask_src > 0)."""
+    """(hi, lo, masked): hi = rn_tf32(v), lo = rn_tf32(v - hi) as fp32 [rows, cols]; v = x or x * (mask_src > 0).
+    lo is None under ``single_product``."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 4 == 0):
         raise ValueError(f"split_tf32: expected a CUDA fp32 row-major matrix with cols % 4 == 0, got {tuple(x.shape)} {x.dtype}")
     rows, cols = x.shape
     hi = torch.empty(rows, cols, device=x.device, dtype=torch.float32)
-    lo = torch.empty(rows, cols, device=x.device, dtype=torch.float32)
+    lo = None if single_product else torch.empty(rows, cols, device=x.device, dtype=torch.float32)
     masked = torch.empty(rows, cols, device=x.device, dtype=torch.float32) if (want_masked and mask_src is not None) else None
     lib = _lib.load()
     _lib.check(lib.wsage_split_tf32(_ptr(x), x.stride(0), _ptr(mask_src), mask_src.stride(0) if mask_src is not None else 0,
@@ -43,7 +48,7 @@ def linear_tc(a_hi, a_lo, b_hi, b_lo, m, n, k, bias=None, relu=False):
     for n0 in range(0, n, step):
         nc = min(step, n - n0)
         o = out[:, n0:n0 + nc]
-        _lib.check(lib.wsage_linear_tc(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi[n0:]), _ptr(b_lo[n0:]), b_hi.stride(0),
+        _lib.check(lib.wsage_linear_tc(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(b_hi[n0:]), _ptr(b_lo[n0:]) if b_lo is not None else None, b_hi.stride(0),
                                        _ptr(bias[n0:]) if bias is not None else None, 1 if relu else 0,
                                        _ptr(o), out.stride(0), m, nc, k, _stream()), "wsage_linear_tc")
     return out

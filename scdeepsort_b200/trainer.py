@@ -41,14 +41,19 @@ class Trainer:
         n = graph.number_of_nodes()
         self.num_neighbors = n if num_neighbors == 0 else num_neighbors        # train.py:37-40
         self.save_path = Path(save_path) if save_path else None
+        # the reference draws fresh neighbour samples every epoch from the process-wide RNG: the device sampler is keyed
+        # by (seed, batch, hop, node), so every epoch gets its own seed, derived from torch's seed (random_seed)
+        self._sample_seed = int(torch.initial_seed()) & 0x7FFFFFFF
+        self._epoch = 0
 
     def train(self):
         """train.py:68-89."""
         self.model.train()
         total = torch.zeros((), device=self.device)
+        self._epoch += 1
         for nf in NeighborSampler(g=self.graph, batch_size=self.batch_size, expand_factor=self.num_neighbors,
                                   num_hops=self.n_layers, neighbor_type='in', shuffle=True, num_workers=8,
-                                  seed_nodes=self.train_ids):
+                                  seed_nodes=self.train_ids, seed=self._sample_seed + 7919 * self._epoch):
             nf.copy_from_parent()
             logits = self.model(nf)
             batch_nids = nf.layer_parent_nid(-1)

@@ -41,3 +41,14 @@ def test_adam_matches_torch_over_steps():
     assert set(sd1["state"][0]) >= {"step", "exp_avg", "exp_avg_sq"}
     assert sd1["param_groups"][0]["lr"] == sd2["param_groups"][0]["lr"]
     assert rel_err(sd1["state"][1]["exp_avg_sq"].cpu(), sd2["state"][1]["exp_avg_sq"].cpu()) < 2e-6
+
+
+def test_cross_entropy_out_of_range_label_poisons_loss_without_oob_read():
+    """the -1 of a gene row in ``all_labels`` must not index the logits: the loss becomes NaN instead."""
+    logits = torch.randn(64, 5, device="cuda:0", requires_grad=True)
+    labels = torch.randint(0, 5, (64,), device="cuda:0")
+    assert bool(torch.isfinite(sd.optim.cross_entropy_sum(logits, labels)))
+    for bad in (-1, 5, 10 ** 9):
+        lab = labels.clone()
+        lab[17] = bad
+        assert bool(torch.isnan(sd.optim.cross_entropy_sum(logits, lab)))

@@ -89,3 +89,35 @@ def test_sampled_nodeflow_matches_oracle_on_same_blocks(golden_train, fanouts):
     # a second batch draws a different sample
     nf2 = sampler.build(seeds.to(DEV))
     assert not torch.equal(nf2.block_parent_eid(n_layers - 1), nf.block_parent_eid(n_layers - 1))
+
+
+def test_trainer_draws_new_neighbour_samples_every_epoch(monkeypatch):
+    """train.py:71-78 re-samples with fresh randomness each epoch; the device sampler is keyed by
+    (seed, batch, hop, node), so Trainer must hand every epoch its own seed, and the seed must follow random_seed."""
+    import scipy.sparse as sp
+    from scdeepsort_b200 import trainer as trainer_mod
+    rng = np.random.RandomState(0)
+    x = sp.csr_matrix(np.where(rng.rand(120, 80) < 0.3, rng.rand(120, 80) + 0.1, 0).astype(np.float32))
+    feats = torch.randn(200, 16, generator=torch.Generator().manual_seed(0))
+    graph = sd.DeepSortGraph.from_expression(x, features=feats)
+    labels = torch.cat([torch.full((80,), -1, dtype=torch.int64), torch.randint(0, 3, (120,))])
+    seen = []
+    real = trainer_mod.NeighborSampler
+
+    def spy(*a, **kw):
+        seen.append(kw.get("seed"))
+        return real(*a, **kw)
+
+    monkeypatch.setattr(trainer_mod, "NeighborSampler", spy)
+
+    def epochs(seed):
+        torch.manual_seed(seed)
+        tr = trainer_mod.Trainer(graph, labels, torch.arange(80, 180), torch.arange(180, 200), 3, dense_dim=16, hidden_dim=16,
+                                 n_layers=2, dropout=0.0, batch_size=50, num_neighbors=4, device="cuda:0")
+        del seen[:]
+        tr.train(); tr.train(); tr.train()
+        return list(seen)
+
+    a, b = epochs(1), epochs(2)
+    assert len(set(a)) == 3 and None not in a          # three epochs, three different sampler seeds
+    assert a == epochs(1) and set(a).isdisjoint(b)     # reproducible under the same random_seed, different under another
