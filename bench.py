@@ -453,21 +453,115 @@ def run_sampled(a):
         sizes.append([nf.layer_size(i) for i in range(nf.num_layers)] + [nf.block_size(i) for i in range(nf.num_blocks)])
         return loss
 
+    from scdeepsort_b200 import ops
     for _ in range(a.warmup):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    csamp = ClockSampler(local_rank) if rank == 0 else None
+    if csamp:
+        csamp.start()
     sd._lib.launch_count(reset=True)
-    t0 = time.perf_counter()
+    ops.TIMING = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(a.steps):
         loss = step()
+    e1.record()
     torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    timing, ops.TIMING = ops.TIMING, None
+    launches = sd._lib.launch_count()
+    ms = e0.elapsed_time(e1) / a.steps
+    # ---- end to end: seed ids and labels come from HOST memory every step, the loss goes back (train.py:79-87) ----
+    h_seeds = seeds.cpu().pin_memory()
+    h_lab = labels.cpu().pin_memory()
+    perm = torch.randperm(h_seeds.shape[0], generator=torch.Generator().manual_seed(SEED))
+
+    def e2e_step(i):
+        idx = perm[(i * a.batch) % max(1, h_seeds.shape[0] - a.batch):][:a.batch]
+        batch = h_seeds[idx].pin_memory().to(dev, non_blocking=True)                 # H2D: this step's seed ids
+        lab = h_lab[h_seeds[idx]].pin_memory().to(dev, non_blocking=True)            # H2D: their labels
+        nf = sampler.build(batch)
+        nf.copy_from_parent()
+        loss = sd.optim.cross_entropy_sum(model(nf), lab)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        parallel.allreduce_grads(model)
+        opt.step()
+        return float(loss)                                                           # D2H: loss.item()
+
+    e2e_step(0)
     if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i + 1)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    clocks = csamp.stop() if csamp else None
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    # ---- roofline: the gather kernels of the sampled blocks are the HBM-bound regime (rows come from a 1.2 GB table) ----
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    groups = {}
+    for t in timing:
+        if t["kind"] not in ("block_fwd", "block_bwd"):
+            continue
+        g = groups.setdefault(t["kind"], dict(ms=0.0, n=0, bytes=0))
+        g["ms"] += t["events"][0].elapsed_time(t["events"][1])
+        g["n"] += 1
+        rows = t["n_src"] * t["dim"] * 4
+        if t["kind"] == "block_fwd":        # edges (int32 + fp32) + rowptr + distinct source rows once + destination rows written
+            g["bytes"] += t["edges"] * 8 + (t["n_dst"] + 1) * 8 + rows + t["n_dst"] * t["dim"] * 4
+        else:                                # edges + dOut rows read + dH rows accumulated (read + write) + H rows read for d-alpha
+            g["bytes"] += t["edges"] * 8 + (t["n_dst"] + 1) * 8 + t["n_dst"] * t["dim"] * 4 + (2 * rows if t["need_h"] else 0) + (rows if t["need_a"] else 0)
+    kernels = {k: {"launches": g["n"], "ms_per_launch": g["ms"] / g["n"], "share_of_step": g["ms"] / a.steps / ms,
+                   "algorithmic_gbs": g["bytes"] / g["ms"] / 1e6, "frac_of_hbm_peak": g["bytes"] / g["ms"] / 1e6 / hbm_peak}
+               for k, g in groups.items()}
+    roofline = None
+    if groups:
+        key, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
+        ach = g["bytes"] / g["ms"] / 1e6
+        roofline = {"kernel": "agg_gather_fwd_kernel" if key == "block_fwd" else "agg_gather_bwd_kernel", "bound": "hbm", "achieved": ach,
+                    "peak": hbm_peak, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "ms_per_launch": g["ms"] / g["n"],
+                    "note": "sum over the blocks of a step (the outermost block dominates); the step itself is launch-bound: "
+                            "see share_of_step in kernels"}
+    # ---- CPU baseline: the oracle's literal restatement of models/gnn.py on the SAME sampled blocks, host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import gnn_oracle
+        from oracle.gnn_oracle import OracleBlock, OracleFlow
+        torch.set_num_threads(os.cpu_count())
+        nb = max(8, min(64, a.batch))
+        nf = sampler.build(seeds[:nb])
+        nf.copy_from_parent()
+        blocks = []
+        for b in nf.blocks:
+            deg = (b.rowptr[1:] - b.rowptr[:-1]).cpu()
+            blocks.append(OracleBlock(b.col.cpu().long(), torch.repeat_interleave(torch.arange(b.n_dst), deg), b.weight.cpu(), b.n_src, b.n_dst))
+        flow = OracleFlow([nf.layer_parent_nid(i).cpu() for i in range(nf.num_layers)],
+                          [nf.layers[i].data["id"].reshape(-1).cpu() for i in range(nf.num_layers)],
+                          nf.layers[0].data["features"].cpu(), blocks)
+        params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        copt = torch.optim.Adam(list(params.values()), lr=1e-3, weight_decay=5e-4)
+        lab = labels[nf.layer_parent_nid(-1)].cpu()
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            closs = torch.nn.functional.cross_entropy(gnn_oracle.forward(params, flow, a.genes), lab, reduction="sum")
+            copt.zero_grad()
+            closs.backward()
+            copt.step()
+            ts.append(time.perf_counter() - t0)
+        cpu = {"value": nb / min(ts[1:]), "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"one sampled mini-batch of {nb} seed cells (same sampler, same fan-outs, blocks copied to the host), fwd+bwd+Adam with "
+                         f"the oracle port of models/gnn.py (edge-materialising), best of 2 after 1 warm-up; sampling itself not timed"}
     if rank == 0:
         print(json.dumps({
             "metric": "cells/sec (forward+backward), neighbour-sampled mini-batches", "value": world * a.batch / (ms / 1e3),
@@ -476,8 +570,13 @@ def run_sampled(a):
             "config": {"workload": f"synthetic {a.cells} cells x {a.genes} genes, avg-degree {int(a.deg)}, {a.layers}-layer "
                                    f"hidden={a.hidden}, fan-outs {fanouts}, {a.batch} seed cells per GPU per step, graph replicated",
                        "graph_build_s": build_s, "graph_edges": graph.number_of_edges(),
+                       "l2_policy": "inputs_exceed_l2 (rows are gathered from a 1.2 GB feature table; no explicit flush)",
                        "last_flow_layers_then_blocks": sizes[-1], "final_loss_per_cell": float(loss) / a.batch},
-            "gpu_launches": sd._lib.launch_count(), "roofline": None, "cpu_baseline": None, "e2e": None}))
+            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "e2e": {"value": world * a.batch / (e2e_ms / 1e3), "unit": "cells/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": world * a.batch * 16, "d2h_bytes_per_step": world * 4,
+                    "api": "NeighborSampler.build(seed ids from host) -> GNN(nf) -> cross_entropy_sum -> backward -> Adam.step -> float(loss)"},
+            "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -54,23 +54,31 @@ def linear_tc(a_hi, a_lo, b_hi, b_lo, m, n, k, bias=None, relu=False):
     return out
 
 
+_GW_MAX_IN = 400       # input columns per wsage_grad_w_tc call (thirteen 32-column blocks fill its 3-stage shared-memory ring)
+
+
 def grad_w_tc(g_hi, g_lo, x_hi, x_lo):
-    """dW[n_out, n_in] = g^T x on the tensor cores (MN-major tf32 hi/lo operands, reduction over the rows)."""
+    """dW[n_out, n_in] = g^T x on the tensor cores (MN-major tf32 hi/lo operands, reduction over the rows).  Inputs wider
+    than 400 columns (hidden 800 of BASELINE configs[4]) are produced in column blocks of x — strided views, no copies."""
     rows, n_out = g_hi.shape
     n_in = x_hi.shape[1]
     lib = _lib.load()
     splits = int(lib.wsage_grad_w_splits(rows, n_out))
-    partial = torch.empty(splits, n_out, n_in, device=g_hi.device, dtype=torch.float32)
     out = torch.empty(n_out, n_in, device=g_hi.device, dtype=torch.float32)
-    _lib.check(lib.wsage_grad_w_tc(_ptr(g_hi), _ptr(g_lo), g_hi.stride(0), _ptr(x_hi), _ptr(x_lo), x_hi.stride(0),
-                                   rows, n_out, n_in, _ptr(partial), splits, _ptr(out), out.stride(0), _stream()),
-               "wsage_grad_w_tc")
+    blocks = -(-n_in // _GW_MAX_IN)
+    step = -(-n_in // blocks)
+    step += -step % 4
+    partial = torch.empty(splits, n_out, min(step, n_in), device=g_hi.device, dtype=torch.float32)
+    for c0 in range(0, n_in, step):
+        nc = min(step, n_in - c0)
+        _lib.check(lib.wsage_grad_w_tc(_ptr(g_hi), _ptr(g_lo), g_hi.stride(0), _ptr(x_hi[:, c0:]), _ptr(x_lo[:, c0:]) if x_lo is not None else None,
+                                       x_hi.stride(0), rows, n_out, nc, _ptr(partial), splits, _ptr(out[:, c0:]), out.stride(0), _stream()),
+                   "wsage_grad_w_tc")
     return out
 
 
 def grad_w_supported(rows: int, n_out: int, n_in: int) -> bool:
-    # n_in <= 416: thirteen 32-column blocks of x per stage is what the 3-stage shared-memory ring holds
-    return rows > 0 and n_out % 4 == 0 and n_in % 4 == 0 and 0 < n_in <= 416 and n_out > 0
+    return rows > 0 and n_out % 4 == 0 and n_in % 4 == 0 and n_in > 0 and n_out > 0
 
 
 def tc_supported(in_features: int, out_features: int) -> bool:

@@ -19,6 +19,19 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _timed(record, fn):
+    """Runs fn(); with bench.py's TIMING list set, brackets it with CUDA events on the launching stream."""
+    if TIMING is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    record["events"] = (e0, e1)
+    TIMING.append(record)
+    return r
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -69,11 +82,12 @@ class _BlockAggregate(torch.autograd.Function):
         dim = h.shape[1]
         out = torch.empty(block.n_dst, dim, device=h.device, dtype=torch.float32)
         lib = _lib.load()
-        _lib.check(lib.wsage_block_agg_fwd(_ptr(block.rowptr), _ptr(block.col), _ptr(block.weight),
-                                           _ptr(src_id), _ptr(dst_id), _ptr(alpha_flat), gene_num,
-                                           _ptr(h), h.stride(0), block.n_src,
-                                           _ptr(out), out.stride(0), block.n_dst, dim, _stream()),
-                   "wsage_block_agg_fwd")
+        rec = dict(kind="block_fwd", edges=int(block.col.shape[0]), n_src=block.n_src, n_dst=block.n_dst, dim=dim)
+        _timed(rec, lambda: _lib.check(lib.wsage_block_agg_fwd(_ptr(block.rowptr), _ptr(block.col), _ptr(block.weight),
+                                                               _ptr(src_id), _ptr(dst_id), _ptr(alpha_flat), gene_num,
+                                                               _ptr(h), h.stride(0), block.n_src,
+                                                               _ptr(out), out.stride(0), block.n_dst, dim, _stream()),
+                                       "wsage_block_agg_fwd"))
         ctx.save_for_backward(h, alpha_flat, src_id, dst_id)
         ctx.block, ctx.gene_num, ctx.alpha_shape = block, gene_num, alpha.shape
         return out
@@ -88,12 +102,14 @@ class _BlockAggregate(torch.autograd.Function):
         da = torch.zeros_like(alpha_flat) if need_a else None
         if need_h or need_a:
             lib = _lib.load()
-            _lib.check(lib.wsage_block_agg_bwd(_ptr(block.rowptr), _ptr(block.col), _ptr(block.weight),
-                                               _ptr(src_id), _ptr(dst_id), _ptr(alpha_flat), ctx.gene_num,
-                                               _ptr(h), h.stride(0), block.n_src,
-                                               _ptr(d_out), d_out.stride(0), block.n_dst, h.shape[1],
-                                               _ptr(dh), dh.stride(0) if need_h else 0, _ptr(da), _stream()),
-                       "wsage_block_agg_bwd")
+            rec = dict(kind="block_bwd", edges=int(block.col.shape[0]), n_src=block.n_src, n_dst=block.n_dst, dim=h.shape[1],
+                       need_h=bool(need_h), need_a=bool(need_a))
+            _timed(rec, lambda: _lib.check(lib.wsage_block_agg_bwd(_ptr(block.rowptr), _ptr(block.col), _ptr(block.weight),
+                                                                   _ptr(src_id), _ptr(dst_id), _ptr(alpha_flat), ctx.gene_num,
+                                                                   _ptr(h), h.stride(0), block.n_src,
+                                                                   _ptr(d_out), d_out.stride(0), block.n_dst, h.shape[1],
+                                                                   _ptr(dh), dh.stride(0) if need_h else 0, _ptr(da), _stream()),
+                                           "wsage_block_agg_bwd"))
         return dh, (da.reshape(ctx.alpha_shape) if need_a else None), None, None, None, None
 
 
@@ -135,19 +151,6 @@ class Csr:
     @property
     def nnz(self):
         return int(self.x.shape[0])
-
-
-def _timed(record, fn):
-    """Runs fn(); with bench.py's TIMING list set, brackets it with CUDA events on the launching stream."""
-    if TIMING is None:
-        return fn()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    r = fn()
-    e1.record()
-    record["events"] = (e0, e1)
-    TIMING.append(record)
-    return r
 
 
 def amax_split16(x, fmt, *, row_ids=None, rowscale=None, layout=_lib.SPLIT_ROWS):

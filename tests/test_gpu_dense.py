@@ -70,7 +70,7 @@ def test_unsupported_shapes_are_rejected():
 
 
 @pytest.mark.parametrize("rows,n_out,n_in", [(5000, 400, 400), (777, 16, 400), (3001, 200, 400), (3000, 400, 200),
-                                             (150000, 400, 400), (40, 8, 32), (20000, 132, 260), (15, 512, 416)])
+                                             (150000, 400, 400), (40, 8, 32), (20000, 132, 260), (15, 512, 416), (9000, 800, 800), (2000, 16, 804)])
 def test_grad_w_tc_matches_fp64(rows, n_out, n_in):
     """wsage_grad_w_tc: dW = g^T x with MN-major tf32 hi/lo operands, split over the rows, vs fp64."""
     gen = torch.Generator(device="cpu").manual_seed(rows + n_out + n_in)
@@ -83,3 +83,23 @@ def test_grad_w_tc_matches_fp64(rows, n_out, n_in):
     ref = g.double().t() @ x.double()
     assert rel_err(dw.cpu(), ref.cpu()) < 1.5e-5      # chains of <= 1024 rows: ~7e-6 from the truncating accumulator
     assert torch.equal(dw, dense.grad_w_tc(g_hi, g_lo, x_hi, x_lo))          # split partials added in fixed order
+
+
+def test_single_product_mode_is_tf32_grade():
+    """dense.single_product (the bf16 configuration of bench.py --config c3): lo operands dropped, one tf32 product per
+    k-step — stated tolerance 2e-3 (tf32 keeps 11 significand bits; observed ~3e-4), forward and both gradients."""
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(3000, 400, generator=gen).to(DEV).requires_grad_(True)
+    w = (torch.randn(200, 400, generator=gen) * 0.05).to(DEV).requires_grad_(True)
+    b = torch.randn(200, generator=gen).to(DEV).requires_grad_(True)
+    try:
+        dense.single_product = True
+        y = dense.linear_relu(x, w, b, relu=True)
+        y.square().sum().backward()
+    finally:
+        dense.single_product = False
+    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    y64 = torch.relu(x64 @ w64.t() + b64)
+    y64.square().sum().backward()
+    assert 1e-6 < rel_err(y.detach().cpu(), y64.detach().cpu()) < 2e-3
+    assert rel_err(x.grad.cpu(), x64.grad.cpu()) < 5e-3 and rel_err(w.grad.cpu(), w64.grad.cpu()) < 5e-3
