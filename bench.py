@@ -144,7 +144,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = a.cpu_sample_cells
+    n = min(a.cpu_sample_cells, a.cells)
     sec = cpu_reference_steps(a, n, a.steps, a.warmup)
     value = n / sec
     sample = (f"first {n} cells of the atlas (same generator, {a.genes} genes, avg-degree {int(a.deg)}), one "
@@ -373,12 +373,12 @@ def run_ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        n = a.cpu_sample_cells
+        n = min(a.cpu_sample_cells, a.cells)
         sec = cpu_reference_steps(a, n, 1, 1)
         cpu = {"value": n / sec, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"first {n} cells of the same atlas, 1 warm-up + 1 timed full-graph fwd+bwd+Adam step, "
                          f"oracle port (edge-materialising, as models/gnn.py:54-56), torch CPU fp32"}
-        n2 = 8 * n
+        n2 = min(8 * n, a.cells)
         sec2 = cpu_spmm_steps(a, n2, 1, 1)
         cpu["optimised"] = {"value": n2 / sec2, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port, closed form",
                             "sample": f"first {n2} cells, same step without the per-edge message tensor: torch sparse-CSR x "

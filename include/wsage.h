@@ -154,9 +154,9 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
  * wsage_amax:    *amax = max(*amax, max |x[r,c] * rowscale[r]|) over rows r (or row_ids[r]) — caller zero-initialises.
  * wsage_split16: hi/lo = 16-bit split of x[r,c] * rowscale[r] * 2^k(amax), in one of three layouts:
  *                WSAGE_SPLIT_ROWS        planes [rows][ld_out]                     (ld_out % 8 == 0)
- *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns — side 0's H^T
- *                WSAGE_SPLIT_COLBLOCKS   planes [ceil(cols / 32)][ld_out rows][32]: 32-column blocks of 64-byte rows —
- *                                        side 1's H; columns past `cols` in the last block are left unwritten
+ *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns — the H^T operand of
+ *                                        wsage_dense16 (K-major on both sides)
+ *                WSAGE_SPLIT_COLBLOCKS   planes [ceil(cols / 32)][ld_out rows][32]: 32-column blocks of 64-byte rows
  * ------------------------------------------------------------------------------------- */
 #define WSAGE_D16_F16X2 0
 #define WSAGE_D16_BF16  1
@@ -178,9 +178,9 @@ typedef struct wsage_dense16_args {
     int32_t        gene_slots;   /* dense genes (storage: wsage_dense16_slots_pad(gene_slots) slots)     */
     float          x_scale;      /* stored value = x * x_scale (a power of two)                          */
     int32_t        side;
-    const void*    h_hi;         /* side 0: [dim][ld_h] (TRANSPOSED); side 1: [ceil(dim/32)][ld_h][32] (COLBLOCKS) */
+    const void*    h_hi;         /* H^T [dim][ld_h] (WSAGE_SPLIT_TRANSPOSED): columns = dense genes (side 0) / cells (side 1) */
     const void*    h_lo;
-    int64_t        ld_h;         /* side 0: row pitch in elements (% 8 == 0); side 1: rows per column block */
+    int64_t        ld_h;         /* row pitch in elements, multiple of 8, >= gene_slots (side 0) / n_src_cells (side 1) */
     const float*   h_amax;       /* device scalar wsage_split16 scaled by (NULL: unscaled)               */
     int32_t        dim;
     int64_t        n_dst;        /* side 0: destination cells (<= cells)                                 */

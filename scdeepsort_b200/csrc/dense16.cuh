@@ -207,14 +207,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 struct D16Params {
-    int side;                    // 0: cell destinations (K-major operands), 1: gene-slot destinations (MN-major operands)
+    int side;                    // 0: cell destinations (A K-major), 1: gene-slot destinations (A MN-major); B is K-major on both sides
     int terms;                   // 3: hi*hi + lo*hi + hi*lo;  1: single product
     int bf16;
-    int n, n_pad, n1, n2;        // output width, rounded up to 16, MMA N halves
-    int b_boxes, b_box_rows;     // side 0: TMA boxes covering the n_pad rows of B
-    int b_blocks;                // side 1: 32-column blocks of B
-    int stages, stage_bytes, tx_bytes, b_bytes;      // stage_bytes: ring pitch (1 KB multiple); tx_bytes: bytes TMA delivers per stage
-    int m_tiles;                 // destination tiles
+    int n, n_pad, n1, n2;        // output width, rounded up to 16, MMA N halves (n1 <= 256)
+    int stages, stage_bytes, tx_bytes, b_bytes;      // stage_bytes: ring pitch (1 KB multiple); tx_bytes: bytes TMA delivers per stage and CTA
+    int m_tiles;                 // destination tiles of 128 (PAIR: an even number of them is processed, the last one may be empty)
     int nb;                      // 32-slot gene blocks per cell tile of the storage
     int num_kb, chunk_kb;        // k-blocks in all / per accumulation chain
     int n_splits, kb_per_split;  // side 0: 1, num_kb
@@ -228,9 +226,60 @@ struct D16Params {
     int64_t ld_hself;
 };
 
+// ---- CTA-pair (cta_group::2) variants of the TMA / MMA / commit instructions -------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {       // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// loads into THIS CTA's shared memory, transaction bytes counted on an mbarrier that may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar_cluster_addr) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256 over the pair: each CTA contributes its 128 rows of A and its half of B's N rows
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrives (once all prior MMAs of this thread have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// kind::f16 instruction descriptor with a_major / b_major given separately and M = m
+__device__ __forceinline__ uint32_t umma_idesc_f16_ab(int m, int n, int bf16, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// PAIR = false: one CTA per 128-row destination tile (cta_group::1).
+// PAIR = true : clusters of two CTAs on the SMs of one TPC work on two neighbouring destination tiles as ONE M = 256 MMA
+//               (cta_group::2): every CTA stages its own 128 rows of A but only HALF of B's N rows, and the tensor cores of both
+//               SMs read both halves.  Per SM that is 41 KB instead of 67 KB of operands per k-block through L2 -> SM and through
+//               shared memory, which is what bounds the single-CTA form (ncu: 9.0 TB/s L2 -> SM, ~123 of 128 B/clk/SM of shared
+//               memory at 77 % tensor-pipe activity).  Rank 0 of the pair issues the MMAs; both ranks run a TMA producer
+//               (transaction bytes land on rank 0's barrier) and four drain warps for their own half of the accumulator.
+template <bool PAIR>
 __global__ void __launch_bounds__(kD16Threads, 1)
 dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_b1_hi, const __grid_constant__ CUtensorMap map_b1_lo,
+               const __grid_constant__ CUtensorMap map_b2_hi, const __grid_constant__ CUtensorMap map_b2_lo,
                const __grid_constant__ CUtensorMap map_out, const D16Params p) {
     extern __shared__ unsigned char dsmem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
@@ -244,21 +293,33 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_items = p.m_tiles * p.n_splits;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int group = PAIR ? blockIdx.x >> 1 : blockIdx.x;                    // work-item stream of this CTA (pair)
+    const int n_groups = PAIR ? gridDim.x >> 1 : gridDim.x;
+    const int tiles_per_item = PAIR ? 2 : 1;
+    const int m_items = (p.m_tiles + tiles_per_item - 1) / tiles_per_item;     // destination tiles (pairs of tiles) per split
+    const int n_items = m_items * p.n_splits;
     const int a_planes = p.terms == 3 ? 2 : 1;
+    // rows of B (= output columns) this CTA stages for the two MMA column groups
+    const int h1 = PAIR ? p.n1 / 2 : p.n1, h2 = PAIR ? p.n2 / 2 : p.n2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, PAIR ? 8 : 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTcMaxN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTcMaxN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTcMaxN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -266,10 +327,10 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ------------------------------------ TMA producer ------------------------------------
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b1_hi) : "memory");
             int it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int mt = item % p.m_tiles, split = item / p.m_tiles;
+            for (int item = group; item < n_items; item += n_groups) {
+                const int mt = (item % m_items) * tiles_per_item + rank, split = item / m_items;
                 const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % p.stages;
@@ -277,45 +338,70 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = ring + (size_t)s * p.stage_bytes;
                     unsigned char* sb = st + a_planes * kD16ABytes;
-                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.tx_bytes);
+                    // the stage's bytes of BOTH CTAs are counted on rank 0's barrier
+                    const uint32_t bar = PAIR ? mapa_u32(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(PAIR ? 2 * p.tx_bytes : p.tx_bytes));
+                    // A: this CTA's 128 destinations
                     if (p.side == 0) {
                         const int row = (mt * p.nb + kb) * kD16TileM;          // cell tile mt, gene block kb: 8 KB contiguous
-                        tma_load_2d(st, &map_a_hi, 0, row, &full_bar[s]);
-                        if (p.terms == 3) tma_load_2d(st + kD16ABytes, &map_a_lo, 0, row, &full_bar[s]);
-                        for (int j = 0; j < p.b_boxes; ++j) {
-                            const int r0 = j * p.b_box_rows;
-                            tma_load_2d(sb + r0 * 64, &map_b_hi, kb * kD16BlockK, r0, &full_bar[s]);
-                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + r0 * 64, &map_b_lo, kb * kD16BlockK, r0, &full_bar[s]);
+                        if (PAIR) {
+                            tma_load_2d_pair(st, &map_a_hi, 0, row, bar);
+                            if (p.terms == 3) tma_load_2d_pair(st + kD16ABytes, &map_a_lo, 0, row, bar);
+                        } else {
+                            tma_load_2d(st, &map_a_hi, 0, row, &full_bar[s]);
+                            if (p.terms == 3) tma_load_2d(st + kD16ABytes, &map_a_lo, 0, row, &full_bar[s]);
                         }
                     } else {
                         // 32 cells of cell tile kb / 4, gene blocks 4 mt .. 4 mt + 3: four 2 KB pieces of one 32 KB region,
-                        // fetched by ONE 3-D box {32 slots, 32 cells, 4 blocks} (the producer thread is the scarce resource:
+                        // fetched by ONE 3-D box {32 slots, 32 cells, 4 blocks} (the producer thread is a scarce resource:
                         // 34 two-dimensional boxes per stage held this side at 0.69 of the other one)
                         const int row = ((kb >> 2) * p.nb + 4 * mt) * kD16TileM + (kb & 3) * 32;
-                        tma_load_3d(st, &map_a_hi, 0, row, 0, &full_bar[s]);
-                        if (p.terms == 3) tma_load_3d(st + kD16ABytes, &map_a_lo, 0, row, 0, &full_bar[s]);
-                        // B: 32 cells x all column blocks of H, one box {32 columns, 32 cells, b_blocks}
-                        tma_load_3d(sb, &map_b_hi, 0, kb * kD16BlockK, 0, &full_bar[s]);
-                        if (p.terms == 3) tma_load_3d(sb + p.b_bytes, &map_b_lo, 0, kb * kD16BlockK, 0, &full_bar[s]);
+                        if (PAIR) {
+                            tma_load_3d_pair(st, &map_a_hi, 0, row, 0, bar);
+                            if (p.terms == 3) tma_load_3d_pair(st + kD16ABytes, &map_a_lo, 0, row, 0, bar);
+                        } else {
+                            tma_load_3d(st, &map_a_hi, 0, row, 0, &full_bar[s]);
+                            if (p.terms == 3) tma_load_3d(st + kD16ABytes, &map_a_lo, 0, row, 0, &full_bar[s]);
+                        }
+                    }
+                    // B = H^T [n rows][K]: this CTA's rows of the two MMA column groups (all of them without a pair)
+                    const int r1 = rank * h1, r2 = p.n1 + rank * h2;
+                    if (PAIR) {
+                        tma_load_2d_pair(sb, &map_b1_hi, kb * kD16BlockK, r1, bar);
+                        if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes, &map_b1_lo, kb * kD16BlockK, r1, bar);
+                        if (h2 > 0) {
+                            tma_load_2d_pair(sb + h1 * 64, &map_b2_hi, kb * kD16BlockK, r2, bar);
+                            if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes + h1 * 64, &map_b2_lo, kb * kD16BlockK, r2, bar);
+                        }
+                    } else {
+                        tma_load_2d(sb, &map_b1_hi, kb * kD16BlockK, r1, &full_bar[s]);
+                        if (p.terms == 3) tma_load_2d(sb + p.b_bytes, &map_b1_lo, kb * kD16BlockK, r1, &full_bar[s]);
+                        if (h2 > 0) {
+                            tma_load_2d(sb + h1 * 64, &map_b2_hi, kb * kD16BlockK, r2, &full_bar[s]);
+                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + h1 * 64, &map_b2_lo, kb * kD16BlockK, r2, &full_bar[s]);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------ MMA issuer --------------------------------------
-        if (lane == 0) {
-            const uint32_t idesc1 = umma_idesc_f16(p.n1, p.bf16, p.side);
-            const uint32_t idesc2 = umma_idesc_f16(p.n2 > 0 ? p.n2 : 16, p.bf16, p.side);
-            // advance along K by one MMA (16 elements): 32 bytes inside the 64-byte row (K-major) / two 8-row atoms (MN-major)
-            const uint64_t k_step = p.side == 0 ? (uint64_t)(32 >> 4) : (uint64_t)(1024 >> 4);
-            const uint64_t n2_off = p.side == 0 ? (uint64_t)((p.n1 * 64) >> 4) : (uint64_t)(((p.n1 / 32) * kD16BoxMN) >> 4);
+        // ------------------------------------ MMA issuer (rank 0 of a pair) -------------------
+        if (lane == 0 && rank == 0) {
+            const int mma_m = PAIR ? 2 * kD16TileM : kD16TileM;
+            const uint32_t idesc1 = umma_idesc_f16_ab(mma_m, p.n1, p.bf16, p.side, 0);
+            const uint32_t idesc2 = umma_idesc_f16_ab(mma_m, p.n2 > 0 ? p.n2 : 16, p.bf16, p.side, 0);
+            // advance along K by one MMA (16 elements): A: 32 bytes inside the 64-byte row (K-major) / two 8-row atoms (MN-major);
+            // B: 32 bytes inside its 64-byte row
+            const uint64_t a_step = p.side == 0 ? (uint64_t)(32 >> 4) : (uint64_t)(1024 >> 4);
+            const uint64_t b_step = (uint64_t)(32 >> 4);
+            const uint64_t n2_off = (uint64_t)((h1 * 64) >> 4);
             int it = 0, chunk_no = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int split = item / p.m_tiles;
+            for (int item = group; item < n_items; item += n_groups) {
+                const int split = item / m_items;
                 const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb, ++chunk_no) {
                     const int c1 = min(kb1, c0 + p.chunk_kb);
-                    mbar_wait(tmem_empty, (chunk_no & 1) ^ 1);             // the drain warps have emptied the accumulators
+                    mbar_wait(tmem_empty, (chunk_no & 1) ^ 1);             // the drain warps (of both CTAs) have emptied the accumulators
                     tc_fence_after();
                     for (int kb = c0; kb < c1; ++kb, ++it) {
                         const int s = it % p.stages;
@@ -324,34 +410,45 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         tc_fence_after();
                         unsigned char* st = ring + (size_t)s * p.stage_bytes;
                         unsigned char* sb = st + a_planes * kD16ABytes;
-                        uint64_t a_hi, a_lo, b_hi, b_lo;
-                        if (p.side == 0) {
-                            a_hi = umma_desc_sw64(st); a_lo = umma_desc_sw64(st + kD16ABytes);
-                            b_hi = umma_desc_sw64(sb); b_lo = umma_desc_sw64(sb + p.b_bytes);
-                        } else {
-                            a_hi = umma_desc_mn_sw64(st); a_lo = umma_desc_mn_sw64(st + kD16ABytes);
-                            b_hi = umma_desc_mn_sw64(sb); b_lo = umma_desc_mn_sw64(sb + p.b_bytes);
-                        }
+                        uint64_t a_hi, a_lo;
+                        if (p.side == 0) { a_hi = umma_desc_sw64(st); a_lo = umma_desc_sw64(st + kD16ABytes); }
+                        else { a_hi = umma_desc_mn_sw64(st); a_lo = umma_desc_mn_sw64(st + kD16ABytes); }
+                        const uint64_t b_hi = umma_desc_sw64(sb), b_lo = umma_desc_sw64(sb + p.b_bytes);
 #pragma unroll
                         for (int kk = 0; kk < kD16BlockK / kD16UmmaK; ++kk) {
-                            const uint64_t ko = (uint64_t)kk * k_step;
+                            const uint64_t ka = (uint64_t)kk * a_step, kbo = (uint64_t)kk * b_step;
                             const uint32_t acc0 = (kb != c0 || kk != 0) ? 1u : 0u;
-                            tc_mma_f16(tmem_base, a_hi + ko, b_hi + ko, idesc1, acc0);
-                            if (p.terms == 3) {
-                                tc_mma_f16(tmem_base, a_lo + ko, b_hi + ko, idesc1, 1);
-                                tc_mma_f16(tmem_base, a_hi + ko, b_lo + ko, idesc1, 1);
-                            }
-                            if (p.n2 > 0) {
-                                tc_mma_f16(tmem_base + p.n1, a_hi + ko, b_hi + n2_off + ko, idesc2, acc0);
+                            if (PAIR) {
+                                tc_mma_f16_pair(tmem_base, a_hi + ka, b_hi + kbo, idesc1, acc0);
                                 if (p.terms == 3) {
-                                    tc_mma_f16(tmem_base + p.n1, a_lo + ko, b_hi + n2_off + ko, idesc2, 1);
-                                    tc_mma_f16(tmem_base + p.n1, a_hi + ko, b_lo + n2_off + ko, idesc2, 1);
+                                    tc_mma_f16_pair(tmem_base, a_lo + ka, b_hi + kbo, idesc1, 1);
+                                    tc_mma_f16_pair(tmem_base, a_hi + ka, b_lo + kbo, idesc1, 1);
+                                }
+                                if (p.n2 > 0) {
+                                    tc_mma_f16_pair(tmem_base + p.n1, a_hi + ka, b_hi + n2_off + kbo, idesc2, acc0);
+                                    if (p.terms == 3) {
+                                        tc_mma_f16_pair(tmem_base + p.n1, a_lo + ka, b_hi + n2_off + kbo, idesc2, 1);
+                                        tc_mma_f16_pair(tmem_base + p.n1, a_hi + ka, b_lo + n2_off + kbo, idesc2, 1);
+                                    }
+                                }
+                            } else {
+                                tc_mma_f16(tmem_base, a_hi + ka, b_hi + kbo, idesc1, acc0);
+                                if (p.terms == 3) {
+                                    tc_mma_f16(tmem_base, a_lo + ka, b_hi + kbo, idesc1, 1);
+                                    tc_mma_f16(tmem_base, a_hi + ka, b_lo + kbo, idesc1, 1);
+                                }
+                                if (p.n2 > 0) {
+                                    tc_mma_f16(tmem_base + p.n1, a_hi + ka, b_hi + n2_off + kbo, idesc2, acc0);
+                                    if (p.terms == 3) {
+                                        tc_mma_f16(tmem_base + p.n1, a_lo + ka, b_hi + n2_off + kbo, idesc2, 1);
+                                        tc_mma_f16(tmem_base + p.n1, a_hi + ka, b_lo + n2_off + kbo, idesc2, 1);
+                                    }
                                 }
                             }
                         }
-                        tc_commit(&empty_bar[s]);
+                        if (PAIR) tc_commit_pair(&empty_bar[s]); else tc_commit(&empty_bar[s]);
                     }
-                    tc_commit(tmem_full);
+                    if (PAIR) tc_commit_pair(tmem_full); else tc_commit(tmem_full);
                 }
             }
         }
@@ -360,14 +457,16 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int q = warp & 3;                                   // TMEM lane quarter of this warp
         unsigned char* my_stage = staging + (warp - 2) * (2 * 32 * 64);
         const int sw = (lane >> 1) & 3;                           // 64-byte swizzle: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
+        const uint32_t tmem_empty_addr = PAIR ? mapa_u32(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
         float h_inv = p.x_scale_inv;
         if (p.amax) h_inv *= ldexpf(1.f, -d16_scale_exp(*p.amax));
         int chunk_no = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int mt = item % p.m_tiles, split = item / p.m_tiles;
+        for (int item = group; item < n_items; item += n_groups) {
+            const int mt = (item % m_items) * tiles_per_item + rank, split = item / m_items;
             const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int64_t grow = (int64_t)mt * kD16TileM + q * 32 + lane;        // destination row of this thread
             const int out_row = (int)(split * p.rows_per_split + (int64_t)mt * kD16TileM + q * 32);
+            const bool tile_ok = mt < p.m_tiles;                                  // the odd tile out of a pair computes nothing useful
             const bool row_ok = grow < p.m_total;
             float scale = h_inv, sc = 0.f;
             if (p.side == 0 && row_ok) {
@@ -381,7 +480,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 // the previous chain's adds to these rows have been performed (and the staging buffers are free)
                 if (lane == 0) bulk_wait_all();
                 __syncwarp();
-                for (int cb = 0; cb * kD16OutCols < p.n_pad; ++cb) {
+                for (int cb = 0; tile_ok && cb * kD16OutCols < p.n_pad; ++cb) {
                     float v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * kD16OutCols), v);
                     if (cb >= 2) {                                       // the store issued two blocks ago has read this buffer
@@ -415,17 +514,20 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(tmem_empty_addr); else mbar_arrive(tmem_empty);
+                }
             }
         }
         if (lane == 0) bulk_wait_all();
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();       // the peer may still read this CTA's shared memory until its last MMA
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcMaxN));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcMaxN));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcMaxN));
     }
 }
 
@@ -489,16 +591,24 @@ inline int make_map_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
     return WSAGE_OK;
 }
 
-inline int d16_slots_pad(int gene_slots) { return (gene_slots + kD16TileM - 1) / kD16TileM * kD16TileM; }
+// slots are padded to 256: a CTA pair works on two whole tiles of 128 gene slots
+inline int d16_slots_pad(int gene_slots) { return (gene_slots + 2 * kD16TileM - 1) / (2 * kD16TileM) * (2 * kD16TileM); }
 
 struct D16Plan {
+    bool pair;
     int m_tiles, nb, num_kb, chunk_kb, n_splits, kb_per_split;
-    int n_pad, n1, n2, b_boxes, b_box_rows, b_blocks, b_bytes, stage_bytes, tx_bytes, stages;
+    int n_pad, n1, n2, h1, h2, b_bytes, stage_bytes, tx_bytes, stages;
     size_t smem_bytes;
 };
 
-// side 1: cut the cell range into splits of whole chains so that the (tile, split) items fill the 148 SMs evenly
-inline void d16_choose_splits(int m_tiles, int num_kb, int chunk_kb, int& n_splits, int& kb_per_split) {
+// WSAGE_D16_PAIR=0 (env, tuning only) selects the single-CTA form
+inline bool d16_pair_env() {
+    static const bool v = [] { const char* e = getenv("WSAGE_D16_PAIR"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+
+// cut the k range into splits of whole chains so that the (tile, split) work items fill the SMs (or SM pairs) evenly
+inline void d16_choose_splits(int m_items, int units, int num_kb, int chunk_kb, int& n_splits, int& kb_per_split) {
     const int chunks = (num_kb + chunk_kb - 1) / chunk_kb;
     int best = 1;
     double best_eff = -1.0;
@@ -507,9 +617,9 @@ inline void d16_choose_splits(int m_tiles, int num_kb, int chunk_kb, int& n_spli
         const int cps = (chunks + s - 1) / s;
         const int ns = (chunks + cps - 1) / cps;
         if (ns != s) continue;
-        const int64_t items = (int64_t)m_tiles * ns;
-        const int64_t rounds = (items + kNumSMs - 1) / kNumSMs;
-        const double eff = (double)m_tiles * chunks / ((double)kNumSMs * rounds * cps);
+        const int64_t items = (int64_t)m_items * ns;
+        const int64_t rounds = (items + units - 1) / units;
+        const double eff = (double)m_items * chunks / ((double)units * rounds * cps);
         if (eff > best_eff + 0.02) { best_eff = eff; best = s; }           // fewer splits unless clearly better
     }
     const int cps = (chunks + best - 1) / best;
@@ -519,26 +629,27 @@ inline void d16_choose_splits(int m_tiles, int num_kb, int chunk_kb, int& n_spli
 
 inline int d16_plan(const wsage_dense16_args* a, D16Plan& pl) {
     const int terms = a->fmt == WSAGE_D16_F16X2 ? 3 : 1;
+    pl.pair = d16_pair_env();
     pl.nb = d16_slots_pad(a->gene_slots) / kD16BlockK;
     int chunk_rows = a->chunk_rows > 0 ? a->chunk_rows : kD16DefaultChunkRows;
     pl.chunk_kb = (chunk_rows + kD16BlockK - 1) / kD16BlockK;
     pl.n_pad = (a->dim + 15) & ~15;
     pl.n1 = pl.n_pad < 256 ? pl.n_pad : 256;
     pl.n2 = pl.n_pad - pl.n1;
-    pl.b_boxes = (pl.n_pad + 255) / 256;
-    pl.b_box_rows = pl.n_pad / pl.b_boxes;
-    pl.b_blocks = (pl.n_pad + 31) / 32;
+    pl.h1 = pl.pair ? pl.n1 / 2 : pl.n1;          // rows of B a CTA stages for each MMA column group
+    pl.h2 = pl.pair ? pl.n2 / 2 : pl.n2;
+    pl.b_bytes = (pl.h1 + pl.h2) * 64;
+    const int tiles_per_item = pl.pair ? 2 : 1;
+    const int units = pl.pair ? kNumSMs / 2 : kNumSMs;
     if (a->side == 0) {
         pl.m_tiles = (int)((a->n_dst + kD16TileM - 1) / kD16TileM);
         pl.num_kb = (a->gene_slots + kD16BlockK - 1) / kD16BlockK;
         pl.n_splits = 1;
         pl.kb_per_split = pl.num_kb;
-        pl.b_bytes = pl.n_pad * 64;
     } else {
         pl.m_tiles = d16_slots_pad(a->gene_slots) / kD16TileM;
         pl.num_kb = (int)((a->n_src_cells + kD16BlockK - 1) / kD16BlockK);
-        d16_choose_splits(pl.m_tiles, pl.num_kb, pl.chunk_kb, pl.n_splits, pl.kb_per_split);
-        pl.b_bytes = pl.b_blocks * kD16BoxMN;
+        d16_choose_splits((pl.m_tiles + tiles_per_item - 1) / tiles_per_item, units, pl.num_kb, pl.chunk_kb, pl.n_splits, pl.kb_per_split);
     }
     pl.tx_bytes = (terms == 3 ? 2 : 1) * (kD16ABytes + pl.b_bytes);
     pl.stage_bytes = (pl.tx_bytes + 1023) & ~1023;

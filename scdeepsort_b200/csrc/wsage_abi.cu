@@ -210,17 +210,17 @@ static int dense16_validate(const wsage_dense16_args* a, bool need_out = true) {
     WSAGE_REQUIRE(a->dim % 4 == 0 && a->dim <= kTcMaxN, "dim must be a multiple of 4, at most 512");
     WSAGE_REQUIRE(a->x_hi && (a->x_lo || a->fmt == WSAGE_D16_BF16) && a->h_hi && (a->h_lo || a->fmt == WSAGE_D16_BF16) && (a->out || !need_out), "null pointer");
     WSAGE_REQUIRE(a->x_scale > 0.f, "x_scale must be positive");
-    WSAGE_REQUIRE(aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned");
+    WSAGE_REQUIRE(a->ld_h % 8 == 0 && aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned with ld_h % 8 == 0");
     WSAGE_REQUIRE(aligned16(a->x_hi) && aligned16(a->x_lo) && aligned16(a->out), "X planes and out must be 16-byte aligned");
     WSAGE_REQUIRE(a->chunk_rows >= 0, "negative chunk_rows");
     if (a->side == 0) {
         WSAGE_REQUIRE(a->n_dst > 0 && a->n_dst <= a->cells, "side 0 needs 0 < n_dst <= cells");
-        WSAGE_REQUIRE(a->ld_h >= a->gene_slots && a->ld_h % 8 == 0, "side 0: ld_h < gene_slots or ld_h % 8 != 0");
+        WSAGE_REQUIRE(a->ld_h >= a->gene_slots, "side 0: ld_h < gene_slots");
         WSAGE_REQUIRE(a->ld_out >= a->dim && a->ld_out % 4 == 0, "ld_out must be >= dim and a multiple of 4");
         WSAGE_REQUIRE(!a->selfcoef || (a->hself && a->ld_hself >= a->dim && a->ld_hself % 4 == 0 && aligned16(a->hself)), "selfcoef needs a 16-byte aligned hself");
     } else {
         WSAGE_REQUIRE(a->n_src_cells > 0 && a->n_src_cells <= a->cells, "side 1 needs 0 < n_src_cells <= cells");
-        WSAGE_REQUIRE(a->ld_h >= a->n_src_cells, "side 1: ld_h (rows per column block) < n_src_cells");
+        WSAGE_REQUIRE(a->ld_h >= a->n_src_cells, "side 1: ld_h < n_src_cells");
         WSAGE_REQUIRE(!a->dscale && !a->selfcoef, "side 1 writes raw partial sums (epilogue in wsage_spmm)");
     }
     const int64_t storage_rows = ((a->cells + kD16TileM - 1) / kD16TileM) * (d16_slots_pad(a->gene_slots) / kD16BlockK) * kD16TileM;
@@ -247,23 +247,26 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
     const uint64_t storage_rows = (uint64_t)((a->cells + kD16TileM - 1) / kD16TileM) * (uint64_t)pl.nb * kD16TileM;
     const void* x_lo = bf ? a->x_hi : a->x_lo;
     const void* h_lo = bf ? a->h_hi : a->h_lo;
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mo;
+    CUtensorMap ma_hi, ma_lo, mb1_hi, mb1_lo, mb2_hi, mb2_lo, mo;
     const char* what = "wsage_dense16";
     D16Params p{};
     p.side = a->side; p.terms = bf ? 1 : 3; p.bf16 = bf ? 1 : 0;
     p.n = a->dim; p.n_pad = pl.n_pad; p.n1 = pl.n1; p.n2 = pl.n2;
-    p.b_boxes = pl.b_boxes; p.b_box_rows = pl.b_box_rows; p.b_blocks = pl.b_blocks;
     p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tx_bytes = pl.tx_bytes; p.b_bytes = pl.b_bytes;
     p.m_tiles = pl.m_tiles; p.nb = pl.nb; p.num_kb = pl.num_kb; p.chunk_kb = pl.chunk_kb;
     p.n_splits = pl.n_splits; p.kb_per_split = pl.kb_per_split;
     p.amax = bf ? nullptr : a->h_amax;
     p.x_scale_inv = 1.f / a->x_scale;
+    // B = H^T [dim][K], K = gene slots (side 0) or sending cells (side 1): columns past K and rows past dim are zero-filled by TMA
+    const uint64_t k_total = a->side == 0 ? (uint64_t)a->gene_slots : (uint64_t)a->n_src_cells;
+    const uint32_t h2_box = (uint32_t)(pl.h2 > 0 ? pl.h2 : pl.h1);
+    if ((rc = make_map_2d(&mb1_hi, dt, 2, a->h_hi, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.h1, what)) != WSAGE_OK) return rc;
+    if ((rc = make_map_2d(&mb1_lo, dt, 2, h_lo, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.h1, what)) != WSAGE_OK) return rc;
+    if ((rc = make_map_2d(&mb2_hi, dt, 2, a->h_hi, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, h2_box, what)) != WSAGE_OK) return rc;
+    if ((rc = make_map_2d(&mb2_lo, dt, 2, h_lo, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, h2_box, what)) != WSAGE_OK) return rc;
     if (a->side == 0) {
         if ((rc = make_map_2d(&ma_hi, dt, 2, a->x_hi, 32, storage_rows, 64, 32, kD16TileM, what)) != WSAGE_OK) return rc;
         if ((rc = make_map_2d(&ma_lo, dt, 2, x_lo, 32, storage_rows, 64, 32, kD16TileM, what)) != WSAGE_OK) return rc;
-        // B = H^T [dim][gene_slots]: columns past gene_slots and rows past dim are zero-filled by TMA
-        if ((rc = make_map_2d(&mb_hi, dt, 2, a->h_hi, (uint64_t)a->gene_slots, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.b_box_rows, what)) != WSAGE_OK) return rc;
-        if ((rc = make_map_2d(&mb_lo, dt, 2, h_lo, (uint64_t)a->gene_slots, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.b_box_rows, what)) != WSAGE_OK) return rc;
         if ((rc = make_map_2d(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->dim, (uint64_t)a->n_dst, (uint64_t)a->ld_out * 4, kD16OutCols, 32, what)) != WSAGE_OK) return rc;
         p.rows_per_split = 0; p.m_total = a->n_dst;
         p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
@@ -271,18 +274,35 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
         // A: {32 slots, storage rows (64 B apart), 4 gene blocks (128 rows = 8 KB apart)}
         if ((rc = make_map_3d(&ma_hi, dt, a->x_hi, storage_rows, 4, 64, (uint64_t)kD16TileM * 64, 4, what)) != WSAGE_OK) return rc;
         if ((rc = make_map_3d(&ma_lo, dt, x_lo, storage_rows, 4, 64, (uint64_t)kD16TileM * 64, 4, what)) != WSAGE_OK) return rc;
-        // B = H in 32-column blocks [b_blocks][ld_h rows][32]: {32 columns, cells (64 B apart), column blocks (ld_h rows apart)};
-        // rows past n_src_cells are zero-filled by TMA; columns dim .. 32 b_blocks of the last block are never stored
-        if ((rc = make_map_3d(&mb_hi, dt, a->h_hi, (uint64_t)a->n_src_cells, (uint64_t)pl.b_blocks, 64, (uint64_t)a->ld_h * 64, (uint32_t)pl.b_blocks, what)) != WSAGE_OK) return rc;
-        if ((rc = make_map_3d(&mb_lo, dt, h_lo, (uint64_t)a->n_src_cells, (uint64_t)pl.b_blocks, 64, (uint64_t)a->ld_h * 64, (uint32_t)pl.b_blocks, what)) != WSAGE_OK) return rc;
         if ((rc = make_map_2d(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->dim, (uint64_t)pl.n_splits * slots_pad, (uint64_t)a->dim * 4, kD16OutCols, 32, what)) != WSAGE_OK) return rc;
         p.rows_per_split = slots_pad; p.m_total = slots_pad;
     }
-    cudaError_t e = cudaFuncSetAttribute(dense16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tiles_per_item = pl.pair ? 2 : 1;
+    const int64_t items = (int64_t)((pl.m_tiles + tiles_per_item - 1) / tiles_per_item) * pl.n_splits;
+    if (pl.pair) {
+        auto kern = dense16_kernel<true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+        if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(dense16 pair)", cudaGetErrorString(e));
+        const int groups = (int)(items < kNumSMs / 2 ? items : kNumSMs / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * groups));
+        cfg.blockDim = dim3(kD16Threads);
+        cfg.dynamicSmemBytes = pl.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb1_hi, mb1_lo, mb2_hi, mb2_lo, mo, p);
+        if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaLaunchKernelEx(dense16 pair)", cudaGetErrorString(e));
+        return check_launch("dense16 (CTA pairs)");
+    }
+    auto kern = dense16_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaFuncSetAttribute(dense16)", cudaGetErrorString(e));
-    const int64_t items = (int64_t)pl.m_tiles * pl.n_splits;
     const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-    dense16_kernel<<<grid, kD16Threads, pl.smem_bytes, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, p);
+    kern<<<grid, kD16Threads, pl.smem_bytes, st>>>(ma_hi, ma_lo, mb1_hi, mb1_lo, mb2_hi, mb2_lo, mo, p);
     return check_launch("dense16");
 }
 

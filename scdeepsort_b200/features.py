@@ -32,7 +32,7 @@ def _row_sums(csr, device, dim_hint):
     return s[:, 0].contiguous()
 
 
-def pca_gene_features(graph: BipartiteGraph, n_components: int, seed: int = 10086, n_iter: int = 4, oversample: int = 10) -> torch.Tensor:
+def pca_gene_features(graph: BipartiteGraph, n_components: int, seed: int = 10086, n_iter: int = 6, oversample: int = 10) -> torch.Tensor:
     """``PCA(n_components, random_state=seed).fit_transform(X_supportᵀ)``: ``[G, n_components]`` fp32 on the device.
     ``graph`` must hold the RAW expression CSRs (``BipartiteGraph.from_expression``); only support cells take part
     (utils/preprocess.py:196: ``sparse_feat[:support_num]``)."""

@@ -200,7 +200,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
             a.hself, a.ld_hself = _ptr(hself), hself.stride(0)
         a.out, a.ld_out = _ptr(out), out.stride(0)
     else:
-        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, layout=_lib.SPLIT_COLBLOCKS)
+        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, layout=_lib.SPLIT_TRANSPOSED)
         a.n_src_cells = n_src_cells
     a.h_hi, a.h_lo, a.ld_h, a.h_amax = _ptr(h_hi), _ptr(h_lo), ld, _ptr(amax)
     if side == 1:

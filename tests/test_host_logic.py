@@ -227,7 +227,7 @@ def test_densify_splits_expression_matrix_exactly():
     assert bg.densified and 0 < len(bg.dense_genes) < g
     d = bg.cell_csr.dense
     assert d is bg.gene_csr.dense and bg.cell_csr.dense_side == 0 and bg.gene_csr.dense_side == 1      # ONE copy, both directions
-    assert d.slots_pad % 128 == 0 and d.hi.numel() == ((c + 127) // 128) * d.slots_pad * 128 == d.lo.numel()
+    assert d.slots_pad % 256 == 0 and d.hi.numel() == ((c + 127) // 128) * d.slots_pad * 128 == d.lo.numel()
     assert bg.cell_csr.nnz + d.nnz == x.nnz == bg.nnz and bg.gene_csr.nnz == bg.cell_csr.nnz
     np.testing.assert_allclose(_csr_matrix(bg.cell_csr) + csr_dense_matrix(bg.cell_csr).numpy(), full, rtol=2.0 ** -21, atol=0)
     np.testing.assert_allclose(_csr_matrix(bg.gene_csr) + csr_dense_matrix(bg.gene_csr).numpy(), full.T, rtol=2.0 ** -21, atol=0)
@@ -306,7 +306,7 @@ def test_dense16_entry_points_validate_arguments_without_a_gpu():
     import ctypes
     lib = sd._lib.load()
     assert lib.wsage_version() >= 2000
-    assert lib.wsage_dense16_slots_pad(1) == 128 and lib.wsage_dense16_slots_pad(129) == 256 and lib.wsage_dense16_slots_pad(0) == 0
+    assert lib.wsage_dense16_slots_pad(1) == 256 and lib.wsage_dense16_slots_pad(257) == 512 and lib.wsage_dense16_slots_pad(0) == 0
     one = ctypes.c_void_p(16)
     assert lib.wsage_amax(one, 400, None, None, 10, 398, one, None) == sd._lib.EINVAL and b"multiple of 4" in lib.wsage_last_error()
     assert lib.wsage_amax(one, 400, None, None, 10, 400, None, None) == sd._lib.EINVAL
