@@ -154,15 +154,18 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
  * wsage_amax:    *amax = max(*amax, max |x[r,c] * rowscale[r]|) over rows r (or row_ids[r]) — caller zero-initialises.
  * wsage_split16: hi/lo = 16-bit split of x[r,c] * rowscale[r] * 2^k(amax), in one of three layouts:
  *                WSAGE_SPLIT_ROWS        planes [rows][ld_out]                     (ld_out % 8 == 0)
- *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns — the H^T operand of
- *                                        wsage_dense16 (K-major on both sides)
+ *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns
  *                WSAGE_SPLIT_COLBLOCKS   planes [ceil(cols / 32)][ld_out rows][32]: 32-column blocks of 64-byte rows
+ *                WSAGE_SPLIT_KBLOCKS     planes [ceil(rows / 32)][ld_out][32]: transposed, cut into k-blocks of 32 (gathered)
+ *                                        rows — the H^T operand of wsage_dense16: one k-block of all columns is one contiguous
+ *                                        piece.  Entries past `rows` in the last block are zeros; ld_out >= cols.
  * ------------------------------------------------------------------------------------- */
 #define WSAGE_D16_F16X2 0
 #define WSAGE_D16_BF16  1
 #define WSAGE_SPLIT_ROWS        0
 #define WSAGE_SPLIT_TRANSPOSED  1
 #define WSAGE_SPLIT_COLBLOCKS   2
+#define WSAGE_SPLIT_KBLOCKS     3
 
 int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
                int64_t rows, int32_t cols, float* amax, void* stream);
@@ -178,9 +181,9 @@ typedef struct wsage_dense16_args {
     int32_t        gene_slots;   /* dense genes (storage: wsage_dense16_slots_pad(gene_slots) slots)     */
     float          x_scale;      /* stored value = x * x_scale (a power of two)                          */
     int32_t        side;
-    const void*    h_hi;         /* H^T [dim][ld_h] (WSAGE_SPLIT_TRANSPOSED): columns = dense genes (side 0) / cells (side 1) */
+    const void*    h_hi;         /* H^T in k-blocks [ceil(K/32)][ld_h][32] (WSAGE_SPLIT_KBLOCKS); K = dense genes (side 0) / cells (side 1) */
     const void*    h_lo;
-    int64_t        ld_h;         /* row pitch in elements, multiple of 8, >= gene_slots (side 0) / n_src_cells (side 1) */
+    int64_t        ld_h;         /* rows per k-block of the H planes, >= dim rounded up to 16            */
     const float*   h_amax;       /* device scalar wsage_split16 scaled by (NULL: unscaled)               */
     int32_t        dim;
     int64_t        n_dst;        /* side 0: destination cells (<= cells)                                 */

@@ -16,7 +16,7 @@ OK, EINVAL, EUNSUPPORTED, ECUDA = 0, 1, 2, 3
 COL_I32, COL_U16 = 32, 16
 ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 D16_F16X2, D16_BF16 = 0, 1
-SPLIT_ROWS, SPLIT_TRANSPOSED, SPLIT_COLBLOCKS = 0, 1, 2
+SPLIT_ROWS, SPLIT_TRANSPOSED, SPLIT_COLBLOCKS, SPLIT_KBLOCKS = 0, 1, 2, 3
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
            "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_amax", "wsage_split16",

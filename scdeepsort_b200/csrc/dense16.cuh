@@ -119,11 +119,16 @@ split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict_
     }
 }
 
-// gathered and transposed: hi/lo[c, s] = split(x[row_ids[s], c] * rowscale[row_ids[s]] * 2^k)   (side 0: H^T[dim, slots])
+// gathered and transposed: hi/lo[c, s] = split(x[row_ids[s], c] * rowscale[row_ids[s]] * 2^k).
+// kblocks == 0: planes [cols][ld_o] (row c = the rows of x as columns).
+// kblocks != 0: planes [ceil(rows / 32)][ld_o][32] — the K-major B operand of dense16_kernel cut into k-blocks of 32 source
+//   rows, so that one k-block of all `cols` output columns is ONE contiguous piece of memory (a [cols][rows] matrix would be
+//   read as 64-byte granules a whole row pitch apart: 1.5 MB at atlas scale).  Entries of the last block past `rows` are
+//   written as zeros (they meet real entries of X); rows cols .. ld_o of a block are left unwritten (never stored columns).
 __global__ void __launch_bounds__(256)
 split16_transpose_kernel(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__ row_ids, const float* __restrict__ rowscale,
                          int64_t rows, int cols, const float* __restrict__ amax, int fmt,
-                         unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o) {
+                         unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o, int kblocks) {
     __shared__ float tile[32][33];
     const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
@@ -141,11 +146,12 @@ split16_transpose_kernel(const float* __restrict__ x, int64_t ld, const int32_t*
     __syncthreads();
     for (int c = ty; c < 32; c += 8) {
         const int64_t s = s0 + tx;
-        if (c0 + c < cols && s < rows) {
+        if (c0 + c < cols && (s < rows || kblocks)) {
             unsigned short h, l;
-            d16_split(tile[tx][c], fmt, h, l);
-            hi[(int64_t)(c0 + c) * ld_o + s] = h;
-            if (fmt == 0) lo[(int64_t)(c0 + c) * ld_o + s] = l;
+            d16_split(tile[tx][c], fmt, h, l);            // tile is zero past `rows`
+            const int64_t o = kblocks ? ((int64_t)blockIdx.x * ld_o + (c0 + c)) * 32 + tx : (int64_t)(c0 + c) * ld_o + s;
+            hi[o] = h;
+            if (fmt == 0) lo[o] = l;
         }
     }
 }
@@ -214,6 +220,7 @@ struct D16Params {
     int stages, stage_bytes, tx_bytes, b_bytes;      // stage_bytes: ring pitch (1 KB multiple); tx_bytes: bytes TMA delivers per stage and CTA
     int m_tiles;                 // destination tiles of 128 (PAIR: an even number of them is processed, the last one may be empty)
     int nb;                      // 32-slot gene blocks per cell tile of the storage
+    int ld_hb;                   // rows per k-block of the B planes
     int num_kb, chunk_kb;        // k-blocks in all / per accumulation chain
     int n_splits, kb_per_split;  // side 0: 1, num_kb
     int64_t rows_per_split;      // side 1: rows of the output map per split (padded slots)
@@ -364,21 +371,22 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             if (p.terms == 3) tma_load_3d(st + kD16ABytes, &map_a_lo, 0, row, 0, &full_bar[s]);
                         }
                     }
-                    // B = H^T [n rows][K]: this CTA's rows of the two MMA column groups (all of them without a pair)
-                    const int r1 = rank * h1, r2 = p.n1 + rank * h2;
+                    // B = H^T in k-blocks [kb][ld_hb rows][32]: this CTA's rows of the two MMA column groups (all of them
+                    // without a pair), each box one contiguous piece of h x 64 bytes
+                    const int r1 = kb * p.ld_hb + rank * h1, r2 = kb * p.ld_hb + p.n1 + rank * h2;
                     if (PAIR) {
-                        tma_load_2d_pair(sb, &map_b1_hi, kb * kD16BlockK, r1, bar);
-                        if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes, &map_b1_lo, kb * kD16BlockK, r1, bar);
+                        tma_load_2d_pair(sb, &map_b1_hi, 0, r1, bar);
+                        if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes, &map_b1_lo, 0, r1, bar);
                         if (h2 > 0) {
-                            tma_load_2d_pair(sb + h1 * 64, &map_b2_hi, kb * kD16BlockK, r2, bar);
-                            if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes + h1 * 64, &map_b2_lo, kb * kD16BlockK, r2, bar);
+                            tma_load_2d_pair(sb + h1 * 64, &map_b2_hi, 0, r2, bar);
+                            if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes + h1 * 64, &map_b2_lo, 0, r2, bar);
                         }
                     } else {
-                        tma_load_2d(sb, &map_b1_hi, kb * kD16BlockK, r1, &full_bar[s]);
-                        if (p.terms == 3) tma_load_2d(sb + p.b_bytes, &map_b1_lo, kb * kD16BlockK, r1, &full_bar[s]);
+                        tma_load_2d(sb, &map_b1_hi, 0, r1, &full_bar[s]);
+                        if (p.terms == 3) tma_load_2d(sb + p.b_bytes, &map_b1_lo, 0, r1, &full_bar[s]);
                         if (h2 > 0) {
-                            tma_load_2d(sb + h1 * 64, &map_b2_hi, kb * kD16BlockK, r2, &full_bar[s]);
-                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + h1 * 64, &map_b2_lo, kb * kD16BlockK, r2, &full_bar[s]);
+                            tma_load_2d(sb + h1 * 64, &map_b2_hi, 0, r2, &full_bar[s]);
+                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + h1 * 64, &map_b2_lo, 0, r2, &full_bar[s]);
                         }
                     }
                 }

@@ -176,21 +176,21 @@ int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const floa
                   void* hi, void* lo, int64_t ld_out, void* stream) {
     WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     WSAGE_REQUIRE(fmt == WSAGE_D16_F16X2 || fmt == WSAGE_D16_BF16, "unknown fmt");
-    WSAGE_REQUIRE(layout >= WSAGE_SPLIT_ROWS && layout <= WSAGE_SPLIT_COLBLOCKS, "unknown layout");
+    WSAGE_REQUIRE(layout >= WSAGE_SPLIT_ROWS && layout <= WSAGE_SPLIT_KBLOCKS, "unknown layout");
     if (rows == 0) return WSAGE_OK;
     WSAGE_REQUIRE(x && hi && (lo || fmt == WSAGE_D16_BF16), "null pointer");
     WSAGE_REQUIRE(ld >= cols && ld % 4 == 0 && aligned16(x), "x must be 16-byte aligned with ld % 4 == 0");
     WSAGE_REQUIRE(aligned16(hi) && aligned16(lo), "planes must be 16-byte aligned");
-    WSAGE_REQUIRE(layout == WSAGE_SPLIT_COLBLOCKS || ld_out % 8 == 0, "ld_out % 8 != 0");
-    WSAGE_REQUIRE(ld_out >= (layout == WSAGE_SPLIT_ROWS ? (int64_t)cols : rows), "ld_out too small");
-    WSAGE_REQUIRE(layout == WSAGE_SPLIT_TRANSPOSED || !row_ids, "row_ids needs the transposed layout");
+    WSAGE_REQUIRE(layout == WSAGE_SPLIT_COLBLOCKS || layout == WSAGE_SPLIT_KBLOCKS || ld_out % 8 == 0, "ld_out % 8 != 0");
+    WSAGE_REQUIRE(ld_out >= ((layout == WSAGE_SPLIT_ROWS || layout == WSAGE_SPLIT_KBLOCKS) ? (int64_t)cols : rows), "ld_out too small");
+    WSAGE_REQUIRE(layout == WSAGE_SPLIT_TRANSPOSED || layout == WSAGE_SPLIT_KBLOCKS || !row_ids, "row_ids needs a transposed layout");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned short* h = static_cast<unsigned short*>(hi);
     unsigned short* l = static_cast<unsigned short*>(lo);
-    if (layout == WSAGE_SPLIT_TRANSPOSED) {
+    if (layout == WSAGE_SPLIT_TRANSPOSED || layout == WSAGE_SPLIT_KBLOCKS) {
         WSAGE_REQUIRE(rows < ((int64_t)1 << 31) * 32, "too many rows");
         dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-        split16_transpose_kernel<<<grid, 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out);
+        split16_transpose_kernel<<<grid, 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_KBLOCKS ? 1 : 0);
         return check_launch("split16_transpose");
     }
     const int64_t total = rows * (cols / 4);
@@ -210,17 +210,18 @@ static int dense16_validate(const wsage_dense16_args* a, bool need_out = true) {
     WSAGE_REQUIRE(a->dim % 4 == 0 && a->dim <= kTcMaxN, "dim must be a multiple of 4, at most 512");
     WSAGE_REQUIRE(a->x_hi && (a->x_lo || a->fmt == WSAGE_D16_BF16) && a->h_hi && (a->h_lo || a->fmt == WSAGE_D16_BF16) && (a->out || !need_out), "null pointer");
     WSAGE_REQUIRE(a->x_scale > 0.f, "x_scale must be positive");
-    WSAGE_REQUIRE(a->ld_h % 8 == 0 && aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned with ld_h % 8 == 0");
+    WSAGE_REQUIRE(aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned");
+    WSAGE_REQUIRE(a->ld_h >= ((a->dim + 15) & ~15) && a->ld_h < (1 << 20), "ld_h (rows per k-block of the H planes) must cover dim rounded up to 16");
     WSAGE_REQUIRE(aligned16(a->x_hi) && aligned16(a->x_lo) && aligned16(a->out), "X planes and out must be 16-byte aligned");
     WSAGE_REQUIRE(a->chunk_rows >= 0, "negative chunk_rows");
     if (a->side == 0) {
         WSAGE_REQUIRE(a->n_dst > 0 && a->n_dst <= a->cells, "side 0 needs 0 < n_dst <= cells");
-        WSAGE_REQUIRE(a->ld_h >= a->gene_slots, "side 0: ld_h < gene_slots");
+
         WSAGE_REQUIRE(a->ld_out >= a->dim && a->ld_out % 4 == 0, "ld_out must be >= dim and a multiple of 4");
         WSAGE_REQUIRE(!a->selfcoef || (a->hself && a->ld_hself >= a->dim && a->ld_hself % 4 == 0 && aligned16(a->hself)), "selfcoef needs a 16-byte aligned hself");
     } else {
         WSAGE_REQUIRE(a->n_src_cells > 0 && a->n_src_cells <= a->cells, "side 1 needs 0 < n_src_cells <= cells");
-        WSAGE_REQUIRE(a->ld_h >= a->n_src_cells, "side 1: ld_h < n_src_cells");
+
         WSAGE_REQUIRE(!a->dscale && !a->selfcoef, "side 1 writes raw partial sums (epilogue in wsage_spmm)");
     }
     const int64_t storage_rows = ((a->cells + kD16TileM - 1) / kD16TileM) * (d16_slots_pad(a->gene_slots) / kD16BlockK) * kD16TileM;
@@ -257,13 +258,14 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
     p.n_splits = pl.n_splits; p.kb_per_split = pl.kb_per_split;
     p.amax = bf ? nullptr : a->h_amax;
     p.x_scale_inv = 1.f / a->x_scale;
-    // B = H^T [dim][K], K = gene slots (side 0) or sending cells (side 1): columns past K and rows past dim are zero-filled by TMA
-    const uint64_t k_total = a->side == 0 ? (uint64_t)a->gene_slots : (uint64_t)a->n_src_cells;
+    // B = H^T in k-blocks [num_kb][ld_h rows][32] (WSAGE_SPLIT_KBLOCKS): a 2-D tensor of 64-byte rows
+    const uint64_t b_rows = (uint64_t)pl.num_kb * (uint64_t)a->ld_h;
     const uint32_t h2_box = (uint32_t)(pl.h2 > 0 ? pl.h2 : pl.h1);
-    if ((rc = make_map_2d(&mb1_hi, dt, 2, a->h_hi, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.h1, what)) != WSAGE_OK) return rc;
-    if ((rc = make_map_2d(&mb1_lo, dt, 2, h_lo, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, (uint32_t)pl.h1, what)) != WSAGE_OK) return rc;
-    if ((rc = make_map_2d(&mb2_hi, dt, 2, a->h_hi, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, h2_box, what)) != WSAGE_OK) return rc;
-    if ((rc = make_map_2d(&mb2_lo, dt, 2, h_lo, k_total, (uint64_t)a->dim, (uint64_t)a->ld_h * 2, 32, h2_box, what)) != WSAGE_OK) return rc;
+    p.ld_hb = (int)a->ld_h;
+    if ((rc = make_map_2d(&mb1_hi, dt, 2, a->h_hi, 32, b_rows, 64, 32, (uint32_t)pl.h1, what)) != WSAGE_OK) return rc;
+    if ((rc = make_map_2d(&mb1_lo, dt, 2, h_lo, 32, b_rows, 64, 32, (uint32_t)pl.h1, what)) != WSAGE_OK) return rc;
+    if ((rc = make_map_2d(&mb2_hi, dt, 2, a->h_hi, 32, b_rows, 64, 32, h2_box, what)) != WSAGE_OK) return rc;
+    if ((rc = make_map_2d(&mb2_lo, dt, 2, h_lo, 32, b_rows, 64, 32, h2_box, what)) != WSAGE_OK) return rc;
     if (a->side == 0) {
         if ((rc = make_map_2d(&ma_hi, dt, 2, a->x_hi, 32, storage_rows, 64, 32, kD16TileM, what)) != WSAGE_OK) return rc;
         if ((rc = make_map_2d(&ma_lo, dt, 2, x_lo, 32, storage_rows, 64, 32, kD16TileM, what)) != WSAGE_OK) return rc;

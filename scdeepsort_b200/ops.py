@@ -170,6 +170,9 @@ def amax_split16(x, fmt, *, row_ids=None, rowscale=None, layout=_lib.SPLIT_ROWS)
     elif layout == _lib.SPLIT_COLBLOCKS:
         ld = rows
         shape = ((cols + 31) // 32, rows, 32)
+    elif layout == _lib.SPLIT_KBLOCKS:
+        ld = (cols + 15) // 16 * 16
+        shape = ((rows + 31) // 32, ld, 32)
     else:
         ld = (cols + 7) // 8 * 8
         shape = (rows, ld)
@@ -191,7 +194,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
     a.x_hi, a.x_lo, a.fmt, a.cells, a.gene_slots, a.x_scale = _ptr(block.hi), _ptr(block.lo), block.fmt, block.cells, block.gene_slots, block.x_scale
     a.side, a.dim, a.chunk_rows = side, dim, chunk_rows
     if side == 0:
-        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, layout=_lib.SPLIT_TRANSPOSED)
+        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, layout=_lib.SPLIT_KBLOCKS)
         a.n_dst = n_dst
         if out is None:
             out = torch.empty(n_dst, dim, device=dev, dtype=torch.float32)
@@ -200,7 +203,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
             a.hself, a.ld_hself = _ptr(hself), hself.stride(0)
         a.out, a.ld_out = _ptr(out), out.stride(0)
     else:
-        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, layout=_lib.SPLIT_TRANSPOSED)
+        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, layout=_lib.SPLIT_KBLOCKS)
         a.n_src_cells = n_src_cells
     a.h_hi, a.h_lo, a.ld_h, a.h_amax = _ptr(h_hi), _ptr(h_lo), ld, _ptr(amax)
     if side == 1:

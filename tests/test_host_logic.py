@@ -320,7 +320,7 @@ def test_dense16_entry_points_validate_arguments_without_a_gpu():
     assert rc == sd._lib.EINVAL and b"fmt" in lib.wsage_last_error()
     a = sd._lib.Dense16Args()
     a.x_hi = a.x_lo = a.h_hi = a.h_lo = a.out = one
-    a.fmt, a.cells, a.gene_slots, a.x_scale, a.dim, a.ld_h = sd._lib.D16_F16X2, 1000, 200, 1024.0, 400, 760_000
+    a.fmt, a.cells, a.gene_slots, a.x_scale, a.dim, a.ld_h = sd._lib.D16_F16X2, 1000, 200, 1024.0, 400, 400
     a.side, a.n_src_cells = 1, 1000
     n = lib.wsage_dense16_splits(ctypes.byref(a))
     assert n == 1                                   # 1000 cells = one chain of 2048 rows
@@ -332,9 +332,9 @@ def test_dense16_entry_points_validate_arguments_without_a_gpu():
     assert lib.wsage_dense16_splits(ctypes.byref(a)) == 0 and b"n_src_cells" in lib.wsage_last_error()
     a.n_src_cells, a.dim = 760_000, 516
     assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"512" in lib.wsage_last_error()
-    a.dim, a.side, a.n_dst, a.ld_h, a.ld_out = 400, 0, 760_000, 16, 400
-    assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"ld_h < gene_slots" in lib.wsage_last_error()
-    a.ld_h, a.selfcoef = 20_000, one
+    a.dim, a.side, a.n_dst, a.ld_h, a.ld_out = 400, 0, 760_000, 384, 400
+    assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"ld_h" in lib.wsage_last_error()
+    a.ld_h, a.selfcoef = 400, one
     assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"hself" in lib.wsage_last_error()
     a.selfcoef, a.x_scale = None, 0.0
     assert lib.wsage_dense16(ctypes.byref(a), None) == sd._lib.EINVAL and b"x_scale" in lib.wsage_last_error()
