@@ -313,7 +313,7 @@ def test_dense16_entry_points_validate_arguments_without_a_gpu():
     rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, sd._lib.D16_F16X2, 0, one, one, 404, None)
     assert rc == sd._lib.EINVAL and b"ld_out % 8" in lib.wsage_last_error()
     rc = lib.wsage_split16(one, 400, one, None, 10, 400, one, sd._lib.D16_F16X2, 0, one, one, 400, None)
-    assert rc == sd._lib.EINVAL and b"row_ids needs the transposed layout" in lib.wsage_last_error()
+    assert rc == sd._lib.EINVAL and b"row_ids needs a transposed layout" in lib.wsage_last_error()
     rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, sd._lib.D16_F16X2, sd._lib.SPLIT_COLBLOCKS, one, one, 9, None)
     assert rc == sd._lib.EINVAL and b"ld_out too small" in lib.wsage_last_error()
     rc = lib.wsage_split16(one, 400, None, None, 10, 400, one, 7, 0, one, one, 400, None)
