@@ -330,7 +330,7 @@ def run_ours(a):
         traffic = None          # ncu dram bytes per launch, recorded under profiles/ for the c4 shape
         tj = ROOT / "profiles" / "r02_traffic.json"
         if tj.exists() and (a.cells, a.genes, int(a.deg), a.dim, world) == (760_000, 20_000, 2000, 400, 1):
-            traffic = json.loads(tj.read_text()).get("c4", {}).get(f"{key[0]}:{key[1]}")
+            traffic = json.loads(tj.read_text()).get("c4", {}).get(f"{key[0]}:{key[1]}", {}).get("dram_bytes_per_launch")
         if key[0] == "dense16":
             achieved = g["flops"] / g["ms"] / 1e9
             roofline = {"kernel": f"dense16_kernel ({key[1]})", "bound": "tensor", "achieved": achieved, "peak": tc_peak,

@@ -163,13 +163,33 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+// L2 eviction policies: the X planes are read exactly once per pass (evict first), the per-pass operand is re-read by
+// every CTA and the output tiles are re-read by the next chain's reduce-add (evict last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int x, int y) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int x, int y, uint64_t pol) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -245,13 +265,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {    
     return r;
 }
 // loads into THIS CTA's shared memory, transaction bytes counted on an mbarrier that may live in the peer CTA (cluster address)
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster_addr) {
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(bar_cluster_addr) : "memory");
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster_addr, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(bar_cluster_addr), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar_cluster_addr) {
-    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar_cluster_addr) : "memory");
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar_cluster_addr, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar_cluster_addr), "l"(pol) : "memory");
 }
 // D[tmem of both CTAs] (+)= A * B^T with M = 256 over the pair: each CTA contributes its 128 rows of A and its half of B's N rows
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -335,6 +355,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b1_hi) : "memory");
+            const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
             int it = 0;
             for (int item = group; item < n_items; item += n_groups) {
                 const int mt = (item % m_items) * tiles_per_item + rank, split = item / m_items;
@@ -352,11 +373,11 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (p.side == 0) {
                         const int row = (mt * p.nb + kb) * kD16TileM;          // cell tile mt, gene block kb: 8 KB contiguous
                         if (PAIR) {
-                            tma_load_2d_pair(st, &map_a_hi, 0, row, bar);
-                            if (p.terms == 3) tma_load_2d_pair(st + kD16ABytes, &map_a_lo, 0, row, bar);
+                            tma_load_2d_pair(st, &map_a_hi, 0, row, bar, pol_a);
+                            if (p.terms == 3) tma_load_2d_pair(st + kD16ABytes, &map_a_lo, 0, row, bar, pol_a);
                         } else {
-                            tma_load_2d(st, &map_a_hi, 0, row, &full_bar[s]);
-                            if (p.terms == 3) tma_load_2d(st + kD16ABytes, &map_a_lo, 0, row, &full_bar[s]);
+                            tma_load_2d_hint(st, &map_a_hi, 0, row, &full_bar[s], pol_a);
+                            if (p.terms == 3) tma_load_2d_hint(st + kD16ABytes, &map_a_lo, 0, row, &full_bar[s], pol_a);
                         }
                     } else {
                         // 32 cells of cell tile kb / 4, gene blocks 4 mt .. 4 mt + 3: four 2 KB pieces of one 32 KB region,
@@ -364,29 +385,29 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         // 34 two-dimensional boxes per stage held this side at 0.69 of the other one)
                         const int row = ((kb >> 2) * p.nb + 4 * mt) * kD16TileM + (kb & 3) * 32;
                         if (PAIR) {
-                            tma_load_3d_pair(st, &map_a_hi, 0, row, 0, bar);
-                            if (p.terms == 3) tma_load_3d_pair(st + kD16ABytes, &map_a_lo, 0, row, 0, bar);
+                            tma_load_3d_pair(st, &map_a_hi, 0, row, 0, bar, pol_a);
+                            if (p.terms == 3) tma_load_3d_pair(st + kD16ABytes, &map_a_lo, 0, row, 0, bar, pol_a);
                         } else {
-                            tma_load_3d(st, &map_a_hi, 0, row, 0, &full_bar[s]);
-                            if (p.terms == 3) tma_load_3d(st + kD16ABytes, &map_a_lo, 0, row, 0, &full_bar[s]);
+                            tma_load_3d_hint(st, &map_a_hi, 0, row, 0, &full_bar[s], pol_a);
+                            if (p.terms == 3) tma_load_3d_hint(st + kD16ABytes, &map_a_lo, 0, row, 0, &full_bar[s], pol_a);
                         }
                     }
                     // B = H^T in k-blocks [kb][ld_hb rows][32]: this CTA's rows of the two MMA column groups (all of them
                     // without a pair), each box one contiguous piece of h x 64 bytes
                     const int r1 = kb * p.ld_hb + rank * h1, r2 = kb * p.ld_hb + p.n1 + rank * h2;
                     if (PAIR) {
-                        tma_load_2d_pair(sb, &map_b1_hi, 0, r1, bar);
-                        if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes, &map_b1_lo, 0, r1, bar);
+                        tma_load_2d_pair(sb, &map_b1_hi, 0, r1, bar, pol_b);
+                        if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes, &map_b1_lo, 0, r1, bar, pol_b);
                         if (h2 > 0) {
-                            tma_load_2d_pair(sb + h1 * 64, &map_b2_hi, 0, r2, bar);
-                            if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes + h1 * 64, &map_b2_lo, 0, r2, bar);
+                            tma_load_2d_pair(sb + h1 * 64, &map_b2_hi, 0, r2, bar, pol_b);
+                            if (p.terms == 3) tma_load_2d_pair(sb + p.b_bytes + h1 * 64, &map_b2_lo, 0, r2, bar, pol_b);
                         }
                     } else {
-                        tma_load_2d(sb, &map_b1_hi, 0, r1, &full_bar[s]);
-                        if (p.terms == 3) tma_load_2d(sb + p.b_bytes, &map_b1_lo, 0, r1, &full_bar[s]);
+                        tma_load_2d_hint(sb, &map_b1_hi, 0, r1, &full_bar[s], pol_b);
+                        if (p.terms == 3) tma_load_2d_hint(sb + p.b_bytes, &map_b1_lo, 0, r1, &full_bar[s], pol_b);
                         if (h2 > 0) {
-                            tma_load_2d(sb + h1 * 64, &map_b2_hi, 0, r2, &full_bar[s]);
-                            if (p.terms == 3) tma_load_2d(sb + p.b_bytes + h1 * 64, &map_b2_lo, 0, r2, &full_bar[s]);
+                            tma_load_2d_hint(sb + h1 * 64, &map_b2_hi, 0, r2, &full_bar[s], pol_b);
+                            if (p.terms == 3) tma_load_2d_hint(sb + p.b_bytes + h1 * 64, &map_b2_lo, 0, r2, &full_bar[s], pol_b);
                         }
                     }
                 }
@@ -468,6 +489,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t tmem_empty_addr = PAIR ? mapa_u32(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
         float h_inv = p.x_scale_inv;
         if (p.amax) h_inv *= ldexpf(1.f, -d16_scale_exp(*p.amax));
+        const uint64_t pol_out = l2_policy_evict_last();
         int chunk_no = 0;
         for (int item = group; item < n_items; item += n_groups) {
             const int mt = (item % m_items) * tiles_per_item + rank, split = item / m_items;
@@ -515,8 +537,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (first) tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row);
-                        else tma_reduce_add_2d(&map_out, buf, cb * kD16OutCols, out_row);
+                        if (first) tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
+                        else tma_reduce_add_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
                         bulk_commit_group();
                     }
                 }

@@ -76,14 +76,15 @@ class _LayerAggregate(torch.autograd.Function):
             hg = hg * gene_mask                             # dropout of the gene rows (models/gnn.py:62-63)
         off = g if gene_too else 0
         neigh = torch.empty(off + c, h.shape[1], device=h.device, dtype=torch.float32)
-        hs = hg * a[:g, None]                               # α folded into the (small) gene table
+        alpha_g = a[:g].contiguous()                        # α enters as a per-source-row factor of the (small) gene table
         coef_c = graph.mean_c * a[g + 1]
         if cells_ready is None and cell_mask is None:
-            ops.spmm(graph.cell_csr, hs, dscale=graph.mean_c * graph.norm_c, selfcoef=coef_c, hself=hc, out=neigh[off:], algo=algo)
+            ops.spmm(graph.cell_csr, hg, src_scale=alpha_g, dscale=graph.mean_c * graph.norm_c, selfcoef=coef_c, hself=hc,
+                     out=neigh[off:], algo=algo)
         else:
             # hc is still being copied from the host: the gene->cell sum needs only the gene table, so it runs
             # under the copy and the self-loop term is added once the rows have landed
-            ops.spmm(graph.cell_csr, hs, dscale=graph.mean_c * graph.norm_c, out=neigh[off:], algo=algo)
+            ops.spmm(graph.cell_csr, hg, src_scale=alpha_g, dscale=graph.mean_c * graph.norm_c, out=neigh[off:], algo=algo)
             if cells_ready is not None:
                 torch.cuda.current_stream().wait_event(cells_ready)
             if cell_mask is not None:
@@ -122,21 +123,22 @@ class _LayerAggregate(torch.autograd.Function):
         if need_h or need_a:
             # T_g = Σ_c x_cg·(s_c·norm_c·dn_c): the transposed pass; dα_g = <h_g, T_g> is its row-dot epilogue and
             # dh_g = α_g·T_g + s_g·α_G·dn_g its scale / self epilogue
-            dsrc = dn_c * (graph.mean_c * graph.norm_c)[:, None]
             kw = {}
             if need_h:
                 kw = dict(dscale=a[:g].contiguous(), out=dh[:g])
                 if gene_too:
                     kw.update(selfcoef=graph.mean_g * a[g], hself=dn_g)
-            _, _, dot = ops.spmm(graph.transpose_of_cell_csr(), dsrc, q=hg, want_dot=need_a, want_out=need_h, algo=ctx.algo, **kw)
-            del dsrc
+            _, _, dot = ops.spmm(graph.transpose_of_cell_csr(), dn_c, src_scale=graph.mean_c * graph.norm_c, q=hg, want_dot=need_a,
+                                 want_out=need_h, algo=ctx.algo, **kw)
         if need_h:
             if gene_too:
                 # dh_c = X_sup·(s_g·norm_g·α_g·dn_g) + s_c·α_{G+1}·dn_c  (self term fused); test cells send nothing to genes
-                dsrc_g = dn_g * (graph.mean_g * graph.norm_g * a[:g])[:, None]
-                if ctx.sharded:
-                    _all_reduce_(dsrc_g)                    # backward of the forward all-reduce of the raw gene sums
-                ops.spmm(graph.support_cell_csr(), dsrc_g, selfcoef=coef_c[:ns].contiguous(), hself=dn_c[:ns], out=dh[g:g + ns], algo=ctx.algo)
+                scale_g = graph.mean_g * graph.norm_g * a[:g]
+                src, scale = dn_g, scale_g
+                if ctx.sharded:                             # backward of the forward all-reduce of the raw gene sums
+                    src, scale = _all_reduce_(dn_g * scale_g[:, None]), None
+                ops.spmm(graph.support_cell_csr(), src, src_scale=scale, selfcoef=coef_c[:ns].contiguous(), hself=dn_c[:ns],
+                         out=dh[g:g + ns], algo=ctx.algo)
                 if ns < c:
                     torch.mul(dn_c[ns:], coef_c[ns:, None], out=dh[g + ns:])
             else:

@@ -184,7 +184,7 @@ def amax_split16(x, fmt, *, row_ids=None, rowscale=None, layout=_lib.SPLIT_ROWS)
 
 
 def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, dscale=None, selfcoef=None, hself=None,
-            out=None, chunk_rows=0):
+            out=None, chunk_rows=0, src_scale=None):
     """The dense block's share of one pass.  side 0: returns out[n_dst, dim] (= dscale·acc + selfcoef·hself);
     side 1: returns the partial slabs [n_splits, slots_pad, dim] for ``spmm(init=...)``."""
     lib = _lib.load()
@@ -194,7 +194,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
     a.x_hi, a.x_lo, a.fmt, a.cells, a.gene_slots, a.x_scale = _ptr(block.hi), _ptr(block.lo), block.fmt, block.cells, block.gene_slots, block.x_scale
     a.side, a.dim, a.chunk_rows = side, dim, chunk_rows
     if side == 0:
-        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, layout=_lib.SPLIT_KBLOCKS)
+        h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, rowscale=src_scale, layout=_lib.SPLIT_KBLOCKS)
         a.n_dst = n_dst
         if out is None:
             out = torch.empty(n_dst, dim, device=dev, dtype=torch.float32)
@@ -203,7 +203,7 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
             a.hself, a.ld_hself = _ptr(hself), hself.stride(0)
         a.out, a.ld_out = _ptr(out), out.stride(0)
     else:
-        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, layout=_lib.SPLIT_KBLOCKS)
+        h_hi, h_lo, amax, ld = amax_split16(hs[:n_src_cells], block.fmt, rowscale=src_scale, layout=_lib.SPLIT_KBLOCKS)
         a.n_src_cells = n_src_cells
     a.h_hi, a.h_lo, a.ld_h, a.h_amax = _ptr(h_hi), _ptr(h_lo), ld, _ptr(amax)
     if side == 1:
@@ -219,14 +219,21 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
 
 
 def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want_out=True,
-         raw=None, want_raw=False, q=None, want_dot=False, algo=_lib.ALGO_AUTO):
-    """acc = Σ_e x_e·hs[col_e];  out = dscale·acc + selfcoef·hself;  raw = acc;  dot = <acc, q>.
+         raw=None, want_raw=False, q=None, want_dot=False, algo=_lib.ALGO_AUTO, src_scale=None):
+    """acc = Σ_e x_e·src_scale[col_e]·hs[col_e];  out = dscale·acc + selfcoef·hself;  raw = acc;  dot = <acc, q>.
 
     Returns (out, raw, dot) with None for the ones not requested.  Entries held by ``csr.dense`` run on the
-    tensor-core kernel first; the CSR walk (or, when the CSR is empty, a plain reduction) adds the rest."""
+    tensor-core kernel first; the CSR walk (or, when the CSR is empty, a plain reduction) adds the rest.
+    ``src_scale`` (optional, one factor per source row) is folded into the dense block's operand split; only a CSR
+    remainder needs the scaled table materialised."""
     _check_mat(hs, "hs", csr.n_src)
     dim = hs.shape[1]
     dev = hs.device
+    if src_scale is not None:
+        _check_vec(src_scale, "src_scale", torch.float32, csr.n_src)
+        if csr.dense is None or csr.nnz > 0:
+            hs = hs * src_scale[:, None]
+            src_scale = None
     if dscale is not None:
         _check_vec(dscale, "dscale", torch.float32, csr.n_dst)
     if selfcoef is not None:
@@ -242,11 +249,11 @@ def spmm(csr: Csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want
         if csr.dense_side == 0:
             direct = csr.nnz == 0 and out is not None and raw is None and not want_raw and not want_dot
             if direct:      # the whole pass is the dense block: its last drain applies the epilogue
-                dense16(d, 0, hs, n_dst=csr.n_dst, dscale=dscale, selfcoef=selfcoef, hself=hself, out=out)
+                dense16(d, 0, hs, n_dst=csr.n_dst, dscale=dscale, selfcoef=selfcoef, hself=hself, out=out, src_scale=src_scale)
                 return out, None, None
-            init = dense16(d, 0, hs, n_dst=csr.n_dst).unsqueeze(0)
+            init = dense16(d, 0, hs, n_dst=csr.n_dst, src_scale=src_scale).unsqueeze(0)
         else:
-            init = dense16(d, 1, hs, n_src_cells=csr.n_src)
+            init = dense16(d, 1, hs, n_src_cells=csr.n_src, src_scale=src_scale)
             init_map = d.slot_of_gene
     if want_raw and raw is None:
         raw = torch.empty(csr.n_dst, dim, device=dev, dtype=torch.float32)

@@ -24,7 +24,9 @@ def _cols(csr):
 
 
 def _spmm_cpu(csr, hs, *, dscale=None, selfcoef=None, hself=None, out=None, want_out=True, raw=None,
-              want_raw=False, q=None, want_dot=False, algo=0):
+              want_raw=False, q=None, want_dot=False, algo=0, src_scale=None):
+    if src_scale is not None:
+        hs = hs * src_scale[:, None]
     seg = torch.repeat_interleave(torch.arange(csr.n_dst), csr.rowptr[1:] - csr.rowptr[:-1])
     acc = torch.zeros(csr.n_dst, hs.shape[1]).index_add_(0, seg, hs[_cols(csr)] * csr.x[:, None])
     if getattr(csr, "dense", None) is not None:      # what wsage_dense16 + wsage_spmm(init=...) add: the block's entries
