@@ -156,6 +156,8 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
  *                WSAGE_SPLIT_ROWS        planes [rows][ld_out]                     (ld_out % 8 == 0)
  *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns
  *                WSAGE_SPLIT_COLBLOCKS   planes [ceil(cols / 32)][ld_out rows][32]: 32-column blocks of 64-byte rows
+ *                WSAGE_SPLIT_BLOCKED     planes [ceil(rows / 128)][ld_out / 32][128][32], zero-filled past the matrix: the X-plane
+ *                                        layout of wsage_dense16 for a dense activation / gradient matrix (ld_out = slot padding)
  *                WSAGE_SPLIT_KBLOCKS     planes [ceil(rows / 32)][ld_out][32]: transposed, cut into k-blocks of 32 (gathered)
  *                                        rows — the H^T operand of wsage_dense16: one k-block of all columns is one contiguous
  *                                        piece.  Entries past `rows` in the last block are zeros; ld_out >= cols.
@@ -166,12 +168,26 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
 #define WSAGE_SPLIT_TRANSPOSED  1
 #define WSAGE_SPLIT_COLBLOCKS   2
 #define WSAGE_SPLIT_KBLOCKS     3
+#define WSAGE_SPLIT_BLOCKED     4
 
 int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
                int64_t rows, int32_t cols, float* amax, void* stream);
 int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
                   int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
                   void* hi, void* lo, int64_t ld_out, void* stream);
+/* Same with v = x * (mask_src > 0): the ReLU backward of models/gnn.py:22 fused into the split (row layouts only). */
+int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask,
+                         const int32_t* row_ids, const float* rowscale,
+                         int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
+                         void* hi, void* lo, int64_t ld_out, void* stream);
+/* Bias gradient of a Linear (+ ReLU) layer (autograd through nn.Linear's bias, models/gnn.py:13,21-22):
+ * out[c] = SUM_r x[r,c] * (mask_src[r,c] > 0) (mask_src NULL: plain column sums).  partial: [n_partial][cols] scratch,
+ * added in index order (deterministic).  cols % 4 == 0, cols <= 1024. */
+int wsage_colsum_masked(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask, int64_t rows, int32_t cols,
+                        float* partial, int32_t n_partial, float* out, void* stream);
+/* out[r,:] = SUM_k slabs[k * slab_stride + r * cols ...] in slab order (the split-K slabs of wsage_dense16 side 1). */
+int wsage_sum_slabs(const float* slabs, int32_t n_slabs, int64_t slab_stride, int64_t rows, int32_t cols,
+                    float* out, int64_t ld_out, void* stream);
 
 typedef struct wsage_dense16_args {
     const void*    x_hi;         /* 16-bit planes of X_dense (layout above)                              */
@@ -195,6 +211,11 @@ typedef struct wsage_dense16_args {
     float*         out;          /* side 0: [n_dst, dim] (row pitch below), side 1: contiguous slabs   */
     int64_t        ld_out;
     int32_t        chunk_rows;   /* accumulation chain length, 0 = default (2048)                        */
+    /* The same kernel as the post-aggregate dense layer (NodeUpdate.forward, models/gnn.py:18-25, and its gradients):
+     * X planes = an activation / gradient matrix in the WSAGE_SPLIT_BLOCKED layout, scaled by its own amax. */
+    const float*   x_amax;       /* device scalar the X planes were scaled by (then x_scale is ignored), or NULL */
+    const float*   bias;         /* side 0: [dim] added to every row, or NULL                            */
+    int32_t        relu;         /* side 0: max(., 0); needs the k range to fit one chain                */
 } wsage_dense16_args;
 
 int wsage_dense16_slots_pad(int32_t gene_slots);

@@ -16,10 +16,11 @@ OK, EINVAL, EUNSUPPORTED, ECUDA = 0, 1, 2, 3
 COL_I32, COL_U16 = 32, 16
 ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 D16_F16X2, D16_BF16 = 0, 1
-SPLIT_ROWS, SPLIT_TRANSPOSED, SPLIT_COLBLOCKS, SPLIT_KBLOCKS = 0, 1, 2, 3
+SPLIT_ROWS, SPLIT_TRANSPOSED, SPLIT_COLBLOCKS, SPLIT_KBLOCKS, SPLIT_BLOCKED = 0, 1, 2, 3, 4
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
            "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_amax", "wsage_split16",
+           "wsage_split16_masked", "wsage_sum_slabs", "wsage_colsum_masked",
            "wsage_dense16_slots_pad", "wsage_dense16_splits", "wsage_dense16",
            "wsage_split_tf32", "wsage_linear_tc", "wsage_grad_w_splits", "wsage_grad_w_tc", "wsage_sample_neighbors",
            "wsage_softmax_ce", "wsage_adam_step")
@@ -46,6 +47,7 @@ class Dense16Args(Structure):
         ("h_amax", c_void_p), ("dim", c_int32), ("n_dst", c_int64), ("n_src_cells", c_int64),
         ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
         ("out", c_void_p), ("ld_out", c_int64), ("chunk_rows", c_int32),
+        ("x_amax", c_void_p), ("bias", c_void_p), ("relu", c_int32),
     ]
 
 
@@ -94,6 +96,13 @@ def load():
     lib.wsage_split16.restype = c_int32
     lib.wsage_split16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32,
                                   c_void_p, c_void_p, c_int64, c_void_p]
+    lib.wsage_split16_masked.restype = c_int32
+    lib.wsage_split16_masked.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32,
+                                         c_int32, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.wsage_sum_slabs.restype = c_int32
+    lib.wsage_sum_slabs.argtypes = [c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p]
+    lib.wsage_colsum_masked.restype = c_int32
+    lib.wsage_colsum_masked.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
     lib.wsage_dense16_slots_pad.restype = c_int32
     lib.wsage_dense16_slots_pad.argtypes = [c_int32]
     lib.wsage_dense16_splits.restype = c_int32

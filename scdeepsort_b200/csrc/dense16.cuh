@@ -96,26 +96,100 @@ __device__ __forceinline__ void d16_split(float v, int fmt, unsigned short& hi, 
     }
 }
 
-// rows stay rows: hi/lo[r, c] = split(x[r, c] * rowscale[r] * 2^k).  blocked == 0: planes [rows][ld_o];  blocked != 0:
-// planes [cols / 32][ld_o rows][32] — 32-column blocks of 64-byte rows, the side-1 operand H[cells, dim] of dense16_kernel
-// (one k-block of one column block is then 2 KB of contiguous memory)
+// rows stay rows: hi/lo = split(v[r, c] * rowscale[r] * 2^k) with v = x, or x * (mask_src > 0) (ReLU backward), in one of
+//   layout 0 (ROWS)       planes [rows][ld_o]
+//   layout 2 (COLBLOCKS)  planes [ceil(cols / 32)][ld_o rows][32]: the K-major B operand of dense16_kernel when the k index
+//                         is the COLUMN of x (a weight matrix [n_out][n_in]: no transposition); the columns past `cols` of
+//                         the last block are written as zeros
+//   layout 4 (BLOCKED)    planes [ceil(rows / 128)][ld_o / 32][128][32]: the A-operand layout of dense16_kernel (include/wsage.h)
+//                         for an activation / gradient matrix, ld_o = slot padding; rows and columns past the matrix are zeros
 __global__ void __launch_bounds__(256)
-split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ rowscale, int64_t rows, int cols,
-               const float* __restrict__ amax, int fmt, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o, int blocked) {
+split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ mask_src, int64_t ld_m, const float* __restrict__ rowscale,
+               int64_t rows, int cols, const float* __restrict__ amax, int fmt,
+               unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o, int layout) {
     const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
+    const int64_t rows_p = layout == 4 ? (rows + 127) / 128 * 128 : rows;
+    const int cols_p = layout == 4 ? (int)ld_o : (layout == 2 ? (cols + 31) / 32 * 32 : cols);
+    const int nb = (int)(ld_o / 32);
+    const int64_t n4 = cols_p / 4;
+    const int64_t total = rows_p * n4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows && c < cols) {
+            v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+            if (mask_src) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(mask_src + r * ld_m + c));
+                v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f;
+                v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+            }
+            const float s = scale * (rowscale ? __ldg(rowscale + r) : 1.f);
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        }
+        unsigned short h[4], l[4];
+        d16_split(v.x, fmt, h[0], l[0]); d16_split(v.y, fmt, h[1], l[1]);
+        d16_split(v.z, fmt, h[2], l[2]); d16_split(v.w, fmt, h[3], l[3]);
+        int64_t o;
+        if (layout == 4) o = ((((r >> 7) * nb + (c >> 5)) << 7) + (r & 127)) * 32 + (c & 31);
+        else if (layout == 2) o = ((int64_t)(c >> 5) * ld_o + r) * 32 + (c & 31);
+        else o = r * ld_o + c;
+        *reinterpret_cast<uint2*>(hi + o) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+        if (fmt == 0) *reinterpret_cast<uint2*>(lo + o) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+    }
+}
+
+// amax over v = x * (mask_src > 0) is bounded by amax over x: the ReLU-backward split uses the unmasked amax (a valid scale).
+
+// partial[b, :] = SUM_{r in block b's rows} x[r, :] * (mask_src[r, :] > 0): the bias gradient of a Linear + ReLU layer (column sums
+// of the masked output gradient); the per-block partials are added in block order by sum_slabs_kernel (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_masked_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ mask_src, int64_t ld_m,
+                     int64_t rows, int cols, float* __restrict__ partial) {
+    __shared__ float4 red[256];
+    const int ncg = cols / 4;                              // column groups of 4 (host guarantees ncg <= 256)
+    const int lanes = 256 / ncg;                           // rows in flight per block
+    const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg;
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes) {
+        for (int64_t r = r0 + rl; r < r1; r += lanes) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + cg * 4));
+            if (mask_src) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(mask_src + r * ld_m + cg * 4));
+                v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f;
+                v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+            }
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    }
+    red[threadIdx.x] = a;
+    __syncthreads();
+    if (rl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 t = red[l * ncg + cg];
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        *reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * cols + cg * 4) = a;
+    }
+}
+
+// out[r, :] = SUM_k slabs[k][r, :]  (fixed order): the split-K slabs of a weight gradient
+__global__ void __launch_bounds__(256)
+sum_slabs_kernel(const float* __restrict__ slabs, int n_slabs, int64_t slab_stride, int64_t rows, int cols,
+                 float* __restrict__ out, int64_t ld_out) {
     const int64_t n4 = cols / 4;
     const int64_t total = rows * n4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n4;
         const int c = (int)(i - r * n4) * 4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
-        const float s = scale * (rowscale ? __ldg(rowscale + r) : 1.f);
-        unsigned short h[4], l[4];
-        d16_split(v.x * s, fmt, h[0], l[0]); d16_split(v.y * s, fmt, h[1], l[1]);
-        d16_split(v.z * s, fmt, h[2], l[2]); d16_split(v.w * s, fmt, h[3], l[3]);
-        const int64_t o = blocked ? ((int64_t)(c >> 5) * ld_o + r) * 32 + (c & 31) : r * ld_o + c;
-        *reinterpret_cast<uint2*>(hi + o) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
-        if (fmt == 0) *reinterpret_cast<uint2*>(lo + o) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < n_slabs; ++k) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(slabs + (size_t)k * slab_stride + r * cols + c));
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        *reinterpret_cast<float4*>(out + r * ld_out + c) = a;
     }
 }
 
@@ -246,7 +320,10 @@ struct D16Params {
     int64_t rows_per_split;      // side 1: rows of the output map per split (padded slots)
     int64_t m_total;             // destination rows
     const float* amax;           // device scalar the per-pass operand was scaled by, or null
+    const float* x_amax;         // device scalar the X planes were scaled by (activations as A operand), or null: x_scale_inv
     float x_scale_inv;
+    const float* bias;           // side 0, per output column, added on a tile's first chain; or null
+    int relu;                    // side 0, single chain only: out = max(out, 0)
     const float* dscale;         // side 0 epilogue: out = dscale * acc + selfcoef * hself
     const float* selfcoef;
     const float* hself;
@@ -487,7 +564,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         unsigned char* my_stage = staging + (warp - 2) * (2 * 32 * 64);
         const int sw = (lane >> 1) & 3;                           // 64-byte swizzle: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
         const uint32_t tmem_empty_addr = PAIR ? mapa_u32(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
-        float h_inv = p.x_scale_inv;
+        float h_inv = p.x_amax ? ldexpf(1.f, -d16_scale_exp(*p.x_amax)) : p.x_scale_inv;
         if (p.amax) h_inv *= ldexpf(1.f, -d16_scale_exp(*p.amax));
         const uint64_t pol_out = l2_policy_evict_last();
         int chunk_no = 0;
@@ -529,6 +606,19 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 v[j * 4 + 2] = fmaf(sc, h.z, v[j * 4 + 2]); v[j * 4 + 3] = fmaf(sc, h.w, v[j * 4 + 3]);
                             }
                         }
+                    }
+                    if (first && p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (cb * kD16OutCols + j * 4 < p.n) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cb * kD16OutCols + j * 4));
+                                v[j * 4 + 0] += b.x; v[j * 4 + 1] += b.y; v[j * 4 + 2] += b.z; v[j * 4 + 3] += b.w;
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     unsigned char* buf = my_stage + (cb & 1) * (32 * 64);
 #pragma unroll

@@ -174,30 +174,67 @@ int wsage_amax(const float* x, int64_t ld, const int32_t* row_ids, const float* 
 int wsage_split16(const float* x, int64_t ld, const int32_t* row_ids, const float* rowscale,
                   int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
                   void* hi, void* lo, int64_t ld_out, void* stream) {
+    return wsage_split16_masked(x, ld, nullptr, 0, row_ids, rowscale, rows, cols, amax, fmt, layout, hi, lo, ld_out, stream);
+}
+
+int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask, const int32_t* row_ids, const float* rowscale,
+                         int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
+                         void* hi, void* lo, int64_t ld_out, void* stream) {
     WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
     WSAGE_REQUIRE(fmt == WSAGE_D16_F16X2 || fmt == WSAGE_D16_BF16, "unknown fmt");
-    WSAGE_REQUIRE(layout >= WSAGE_SPLIT_ROWS && layout <= WSAGE_SPLIT_KBLOCKS, "unknown layout");
+    WSAGE_REQUIRE(layout >= WSAGE_SPLIT_ROWS && layout <= WSAGE_SPLIT_BLOCKED, "unknown layout");
     if (rows == 0) return WSAGE_OK;
     WSAGE_REQUIRE(x && hi && (lo || fmt == WSAGE_D16_BF16), "null pointer");
     WSAGE_REQUIRE(ld >= cols && ld % 4 == 0 && aligned16(x), "x must be 16-byte aligned with ld % 4 == 0");
     WSAGE_REQUIRE(aligned16(hi) && aligned16(lo), "planes must be 16-byte aligned");
+    const bool transposed = layout == WSAGE_SPLIT_TRANSPOSED || layout == WSAGE_SPLIT_KBLOCKS;
+    WSAGE_REQUIRE(!mask_src || (!transposed && ld_mask >= cols && ld_mask % 4 == 0 && aligned16(mask_src)), "mask_src needs a row layout and a 16-byte aligned mask");
     WSAGE_REQUIRE(layout == WSAGE_SPLIT_COLBLOCKS || layout == WSAGE_SPLIT_KBLOCKS || ld_out % 8 == 0, "ld_out % 8 != 0");
-    WSAGE_REQUIRE(ld_out >= ((layout == WSAGE_SPLIT_ROWS || layout == WSAGE_SPLIT_KBLOCKS) ? (int64_t)cols : rows), "ld_out too small");
-    WSAGE_REQUIRE(layout == WSAGE_SPLIT_TRANSPOSED || layout == WSAGE_SPLIT_KBLOCKS || !row_ids, "row_ids needs a transposed layout");
+    WSAGE_REQUIRE(layout != WSAGE_SPLIT_BLOCKED || ld_out % 32 == 0, "blocked layout: ld_out (slot padding) must be a multiple of 32");
+    WSAGE_REQUIRE(ld_out >= ((layout == WSAGE_SPLIT_ROWS || layout == WSAGE_SPLIT_KBLOCKS || layout == WSAGE_SPLIT_BLOCKED) ? (int64_t)cols : rows), "ld_out too small");
+    WSAGE_REQUIRE(transposed || !row_ids, "row_ids needs a transposed layout");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned short* h = static_cast<unsigned short*>(hi);
     unsigned short* l = static_cast<unsigned short*>(lo);
-    if (layout == WSAGE_SPLIT_TRANSPOSED || layout == WSAGE_SPLIT_KBLOCKS) {
+    if (transposed) {
         WSAGE_REQUIRE(rows < ((int64_t)1 << 31) * 32, "too many rows");
         dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
         split16_transpose_kernel<<<grid, 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_KBLOCKS ? 1 : 0);
         return check_launch("split16_transpose");
     }
+    const int64_t cols_p = layout == WSAGE_SPLIT_BLOCKED ? ld_out : (cols + 31) / 32 * 32;
+    const int64_t total = (rows + 127) / 128 * 128 * (cols_p / 4);
+    int64_t grid = (total + 255) / 256;
+    if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
+    split16_kernel<<<(int)grid, 256, 0, st>>>(x, ld, mask_src, ld_mask, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout);
+    return check_launch("split16");
+}
+
+int wsage_sum_slabs(const float* slabs, int32_t n_slabs, int64_t slab_stride, int64_t rows, int32_t cols,
+                    float* out, int64_t ld_out, void* stream) {
+    WSAGE_REQUIRE(n_slabs > 0 && rows >= 0 && cols > 0 && cols % 4 == 0, "bad shape");
+    if (rows == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(slabs && out && aligned16(slabs) && aligned16(out), "null or misaligned pointer");
+    WSAGE_REQUIRE(slab_stride >= rows * cols && slab_stride % 4 == 0 && ld_out >= cols && ld_out % 4 == 0, "bad stride");
     const int64_t total = rows * (cols / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    split16_kernel<<<(int)grid, 256, 0, st>>>(x, ld, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_COLBLOCKS ? 1 : 0);
-    return check_launch("split16");
+    sum_slabs_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(slabs, n_slabs, slab_stride, rows, cols, out, ld_out);
+    return check_launch("sum_slabs");
+}
+
+int wsage_colsum_masked(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask, int64_t rows, int32_t cols,
+                        float* partial, int32_t n_partial, float* out, void* stream) {
+    WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4, at most 1024");
+    WSAGE_REQUIRE(n_partial >= 1 && partial && out && aligned16(partial) && aligned16(out), "null or misaligned output");
+    WSAGE_REQUIRE(rows == 0 || (x && ld >= cols && ld % 4 == 0 && aligned16(x)), "x must be 16-byte aligned with ld % 4 == 0");
+    WSAGE_REQUIRE(!mask_src || (ld_mask >= cols && ld_mask % 4 == 0 && aligned16(mask_src)), "bad mask");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    colsum_masked_kernel<<<n_partial, 256, 0, st>>>(x, ld, mask_src, ld_mask, rows, cols, partial);
+    int rc = check_launch("colsum_masked");
+    if (rc != WSAGE_OK) return rc;
+    sum_slabs_kernel<<<(cols / 4 + 255) / 256, 256, 0, st>>>(partial, n_partial, cols, 1, cols, out, cols);
+    return check_launch("sum_slabs");
 }
 
 int wsage_dense16_slots_pad(int32_t gene_slots) { return gene_slots > 0 ? d16_slots_pad(gene_slots) : 0; }
@@ -209,7 +246,8 @@ static int dense16_validate(const wsage_dense16_args* a, bool need_out = true) {
     WSAGE_REQUIRE(a->cells > 0 && a->gene_slots > 0 && a->dim > 0, "cells, gene_slots and dim must be positive");
     WSAGE_REQUIRE(a->dim % 4 == 0 && a->dim <= kTcMaxN, "dim must be a multiple of 4, at most 512");
     WSAGE_REQUIRE(a->x_hi && (a->x_lo || a->fmt == WSAGE_D16_BF16) && a->h_hi && (a->h_lo || a->fmt == WSAGE_D16_BF16) && (a->out || !need_out), "null pointer");
-    WSAGE_REQUIRE(a->x_scale > 0.f, "x_scale must be positive");
+    WSAGE_REQUIRE(a->x_scale > 0.f || a->x_amax, "x_scale must be positive (or x_amax given)");
+    WSAGE_REQUIRE(!a->bias || aligned16(a->bias), "bias must be 16-byte aligned");
     WSAGE_REQUIRE(aligned16(a->h_hi) && aligned16(a->h_lo), "H planes must be 16-byte aligned");
     WSAGE_REQUIRE(a->ld_h >= ((a->dim + 15) & ~15) && a->ld_h < (1 << 20), "ld_h (rows per k-block of the H planes) must cover dim rounded up to 16");
     WSAGE_REQUIRE(aligned16(a->x_hi) && aligned16(a->x_lo) && aligned16(a->out), "X planes and out must be 16-byte aligned");
@@ -222,7 +260,7 @@ static int dense16_validate(const wsage_dense16_args* a, bool need_out = true) {
     } else {
         WSAGE_REQUIRE(a->n_src_cells > 0 && a->n_src_cells <= a->cells, "side 1 needs 0 < n_src_cells <= cells");
 
-        WSAGE_REQUIRE(!a->dscale && !a->selfcoef, "side 1 writes raw partial sums (epilogue in wsage_spmm)");
+        WSAGE_REQUIRE(!a->dscale && !a->selfcoef && !a->bias && !a->relu, "side 1 writes raw partial sums (epilogue in wsage_spmm)");
     }
     const int64_t storage_rows = ((a->cells + kD16TileM - 1) / kD16TileM) * (d16_slots_pad(a->gene_slots) / kD16BlockK) * kD16TileM;
     WSAGE_REQUIRE(storage_rows < ((int64_t)1 << 31), "dense block too large for 32-bit TMA coordinates");
@@ -257,7 +295,11 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
     p.m_tiles = pl.m_tiles; p.nb = pl.nb; p.num_kb = pl.num_kb; p.chunk_kb = pl.chunk_kb;
     p.n_splits = pl.n_splits; p.kb_per_split = pl.kb_per_split;
     p.amax = bf ? nullptr : a->h_amax;
-    p.x_scale_inv = 1.f / a->x_scale;
+    p.x_amax = bf ? nullptr : a->x_amax;
+    p.x_scale_inv = a->x_scale > 0.f ? 1.f / a->x_scale : 1.f;
+    p.bias = a->bias; p.relu = a->relu;
+    if (a->relu && pl.num_kb > pl.chunk_kb)
+        return fail(WSAGE_EUNSUPPORTED, "%s: %s", "wsage_dense16", "relu needs the whole k range in one accumulation chain");
     // B = H^T in k-blocks [num_kb][ld_h rows][32] (WSAGE_SPLIT_KBLOCKS): a 2-D tensor of 64-byte rows
     const uint64_t b_rows = (uint64_t)pl.num_kb * (uint64_t)a->ld_h;
     const uint32_t h2_box = (uint32_t)(pl.h2 > 0 ? pl.h2 : pl.h1);

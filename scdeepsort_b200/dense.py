@@ -124,9 +124,154 @@ class _LinearReluTC(torch.autograd.Function):
         if need_w:
             dw = grad_w_tc(g_hi, g_lo, x, x_lo) if ctx.tc_dw else g.t() @ x
         if need_b:
-            db = g.sum(dim=0)
+            db = colsum_masked(g)
         return dx, dw, db, None
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The same layer on the dense16 GEMM (csrc/dense16.cuh): fp16 hi+lo operands, three products — the precision grade of the
+# tf32x3 kernels above at twice the MMA rate and half the operand bytes; bf16 (one product) under ``single_product``.
+#   forward   out = act(x W^T + b)   side 0: A = BLOCKED(x),      B = COLBLOCKS(W)  (k = in-feature  = column of W)
+#   dx        = g W                   side 0: A = BLOCKED(g),      B = KBLOCKS(W)    (k = out-feature = row of W)
+#   dW        = g^T x                 side 1: A = BLOCKED(g) (its columns are the destination slots), B = KBLOCKS(x)
+# ---------------------------------------------------------------------------------------------------------------------
+use_dense16 = True          # False: the tf32x3 kernels (wsage_linear_tc / wsage_grad_w_tc)
+_D16_MAX_N = 512
+
+
+def _fmt():
+    return _lib.D16_BF16 if single_product else _lib.D16_F16X2
+
+
+def _amax(x, fmt):
+    if fmt != _lib.D16_F16X2:
+        return None
+    amax = torch.zeros(1, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().wsage_amax(_ptr(x), x.stride(0), None, None, x.shape[0], x.shape[1], _ptr(amax), _stream()), "wsage_amax")
+    return amax
+
+
+def _split(x, fmt, layout, ld, shape, amax, mask_src=None):
+    hi = torch.empty(shape, device=x.device, dtype=torch.int16)
+    lo = torch.empty(shape, device=x.device, dtype=torch.int16) if fmt == _lib.D16_F16X2 else None
+    _lib.check(_lib.load().wsage_split16_masked(_ptr(x), x.stride(0), _ptr(mask_src), mask_src.stride(0) if mask_src is not None else 0,
+                                                None, None, x.shape[0], x.shape[1], _ptr(amax), fmt, layout, _ptr(hi), _ptr(lo), ld,
+                                                _stream()), "wsage_split16")
+    return hi, lo
+
+
+def _planes_a(x, fmt, mask_src=None):
+    """BLOCKED planes of a [rows, k] matrix: (hi, lo, amax, rows, k)."""
+    rows, k = x.shape
+    pad = int(_lib.load().wsage_dense16_slots_pad(k))
+    amax = _amax(x, fmt)
+    hi, lo = _split(x, fmt, _lib.SPLIT_BLOCKED, pad, ((rows + 127) // 128 * pad * 128,), amax, mask_src)
+    return hi, lo, amax, rows, k
+
+
+def _planes_b(x, fmt, k_is_row):
+    """B planes [ceil(K / 32)][ceil16(N)][32] of a matrix whose k index is its row (KBLOCKS) or its column (COLBLOCKS)."""
+    rows, cols = x.shape
+    amax = _amax(x, fmt)
+    if k_is_row:
+        ld = (cols + 15) // 16 * 16
+        hi, lo = _split(x, fmt, _lib.SPLIT_KBLOCKS, ld, ((rows + 31) // 32, ld, 32), amax)
+    else:
+        ld = (rows + 15) // 16 * 16
+        hi, lo = _split(x, fmt, _lib.SPLIT_COLBLOCKS, ld, ((cols + 31) // 32, ld, 32), amax)
+    return hi, lo, amax, ld
+
+
+def _gemm16(a, b, fmt, side, dim, out, *, bias=None, relu=False, n_splits_out=None):
+    """One wsage_dense16 call with activation planes as the X operand."""
+    a_hi, a_lo, a_amax, rows, k = a
+    b_hi, b_lo, b_amax, ld = b
+    lib = _lib.load()
+    args = _lib.Dense16Args()
+    args.x_hi, args.x_lo, args.fmt, args.cells, args.gene_slots, args.x_scale = _ptr(a_hi), _ptr(a_lo), fmt, rows, k, 1.0
+    args.x_amax, args.side, args.dim = _ptr(a_amax), side, dim
+    args.h_hi, args.h_lo, args.ld_h, args.h_amax = _ptr(b_hi), _ptr(b_lo), ld, _ptr(b_amax)
+    if side == 0:
+        args.n_dst, args.bias, args.relu = rows, _ptr(bias), 1 if relu else 0
+        args.out, args.ld_out = _ptr(out), out.stride(0)
+    else:
+        args.n_src_cells = rows
+        n_splits = int(lib.wsage_dense16_splits(ctypes.byref(args)))
+        if n_splits <= 0:
+            _lib.check(_lib.EINVAL, "wsage_dense16_splits")
+        pad = int(lib.wsage_dense16_slots_pad(k))
+        out = torch.empty(n_splits, pad, dim, device=a_hi.device, dtype=torch.float32)
+        args.out, args.ld_out = _ptr(out), dim
+    _lib.check(lib.wsage_dense16(ctypes.byref(args), _stream()), "wsage_dense16")
+    return out
+
+
+def colsum_masked(x, mask_src=None):
+    """Column sums of x * (mask_src > 0): the bias gradient (deterministic two-stage sum on the device)."""
+    rows, cols = x.shape
+    if cols % 4 or cols > 1024:
+        return (x if mask_src is None else x * (mask_src > 0)).sum(dim=0)
+    n_partial = max(1, min(148 * 4, (rows + 63) // 64))
+    partial = torch.empty(n_partial, cols, device=x.device, dtype=torch.float32)
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().wsage_colsum_masked(_ptr(x), x.stride(0), _ptr(mask_src), mask_src.stride(0) if mask_src is not None else 0,
+                                               rows, cols, _ptr(partial), n_partial, _ptr(out), _stream()), "wsage_colsum_masked")
+    return out
+
+
+class _LinearReluD16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x = x.contiguous()
+        w = weight.contiguous()
+        m, k = x.shape
+        n = w.shape[0]
+        fmt = _fmt()
+        a = _planes_a(x, fmt)
+        y = torch.empty(m, n, device=x.device, dtype=torch.float32)
+        for n0 in range(0, n, _D16_MAX_N):
+            n1 = min(n, n0 + _D16_MAX_N)
+            _gemm16(a, _planes_b(w[n0:n1], fmt, k_is_row=False), fmt, 0, n1 - n0, y[:, n0:n1],
+                    bias=bias[n0:n1].contiguous() if bias is not None else None, relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu, ctx.fmt = relu, fmt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dy = dy.contiguous()
+        m, n = dy.shape
+        k = x.shape[1]
+        fmt = ctx.fmt
+        dx = dw = db = None
+        if need_x or need_w:
+            g = _planes_a(dy, fmt, mask_src=y if ctx.relu else None)          # g = dy * (y > 0), split into A planes
+        if need_x:
+            dx = torch.empty(m, k, device=dy.device, dtype=torch.float32)
+            for k0 in range(0, k, _D16_MAX_N):
+                k1 = min(k, k0 + _D16_MAX_N)
+                _gemm16(g, _planes_b(w[:, k0:k1].contiguous(), fmt, k_is_row=True), fmt, 0, k1 - k0, dx[:, k0:k1])
+        if need_w:
+            dw = torch.empty(n, k, device=dy.device, dtype=torch.float32)
+            lib = _lib.load()
+            for k0 in range(0, k, _D16_MAX_N):
+                k1 = min(k, k0 + _D16_MAX_N)
+                xs = x if (k0 == 0 and k1 == k) else x[:, k0:k1].contiguous()
+                slabs = _gemm16(g, _planes_b(xs, fmt, k_is_row=True), fmt, 1, k1 - k0, None)
+                _lib.check(lib.wsage_sum_slabs(_ptr(slabs), slabs.shape[0], slabs.shape[1] * slabs.shape[2], n, k1 - k0,
+                                               _ptr(dw[:, k0:k1]), dw.stride(0), _stream()), "wsage_sum_slabs")
+        if need_b:
+            db = colsum_masked(dy, y if ctx.relu else None)
+        return dx, dw, db, None
+
+
+def d16_supported(in_features: int, out_features: int) -> bool:
+    return in_features % 4 == 0 and out_features % 4 == 0 and in_features > 0 and out_features > 0
+
+
 def linear_relu(x, weight, bias=None, relu=True):
+    if use_dense16 and d16_supported(weight.shape[1], weight.shape[0]):
+        return _LinearReluD16.apply(x, weight, bias, relu)
     return _LinearReluTC.apply(x, weight, bias, relu)

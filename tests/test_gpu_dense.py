@@ -1,6 +1,6 @@
-"""GPU parity of the tensor-core dense layer (wsage_split_tf32 + wsage_linear_tc, tf32x3 split) against
-an fp64 torch reference of NodeUpdate (models/gnn.py:18-25).  Tolerance: 1e-4 relative (north_star);
-observed 1e-6 .. 3.4e-6 (fp32-grade)."""
+"""GPU parity of the tensor-core dense layer against an fp64 torch reference of NodeUpdate (models/gnn.py:18-25), on both
+implementations: the dense16 GEMM (fp16 hi+lo operands, three products — the product's default) and the tf32x3 kernels
+(wsage_split_tf32 + wsage_linear_tc + wsage_grad_w_tc).  Tolerance: 1e-4 relative (north_star); observed 1e-6 .. 3.4e-6."""
 import numpy as np
 import pytest
 import torch
@@ -30,8 +30,10 @@ def test_split_tf32_reconstructs_fp32():
                                              (300, 400, 16, False, True), (1, 64, 64, True, True),
                                              (1102, 400, 200, True, True), (259, 48, 40, True, True), (700, 40, 12, False, True),
                                              (3000, 400, 800, True, True), (1500, 800, 800, True, True)])
-def test_linear_tc_forward_backward(m, k, n, relu, bias):
-    assert dense.tc_supported(k, n)
+@pytest.mark.parametrize("impl", ["dense16", "tf32x3"])
+def test_linear_tc_forward_backward(m, k, n, relu, bias, impl, monkeypatch):
+    monkeypatch.setattr(dense, "use_dense16", impl == "dense16")
+    assert dense.tc_supported(k, n) and dense.d16_supported(k, n)
     g = torch.Generator(device="cpu").manual_seed(m + k + n)
     x = torch.randn(m, k, generator=g).to(DEV).requires_grad_(True)
     w = (torch.randn(n, k, generator=g) * 0.1).to(DEV).requires_grad_(True)
@@ -103,3 +105,14 @@ def test_single_product_mode_is_tf32_grade():
     y64.square().sum().backward()
     assert 1e-6 < rel_err(y.detach().cpu(), y64.detach().cpu()) < 2e-3
     assert rel_err(x.grad.cpu(), x64.grad.cpu()) < 5e-3 and rel_err(w.grad.cpu(), w64.grad.cpu()) < 5e-3
+
+
+def test_colsum_masked_matches_torch_and_is_deterministic():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for rows, cols in ((70000, 400), (5, 16), (1234, 800), (129, 1024)):
+        x = torch.randn(rows, cols, generator=g).to(DEV)
+        y = torch.randn(rows, cols, generator=g).to(DEV)
+        got = dense.colsum_masked(x, y)
+        assert rel_err(got.cpu(), (x.double() * (y > 0)).sum(0).cpu()) < 1e-5
+        assert torch.equal(got, dense.colsum_masked(x, y))
+        assert rel_err(dense.colsum_masked(x).cpu(), x.double().sum(0).cpu()) < 1e-5
