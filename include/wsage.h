@@ -185,6 +185,9 @@ int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int6
  * added in index order (deterministic).  cols % 4 == 0, cols <= 1024. */
 int wsage_colsum_masked(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask, int64_t rows, int32_t cols,
                         float* partial, int32_t n_partial, float* out, void* stream);
+/* out[r] = <a[r,:], b[r,:]> (the self-loop terms of the alpha gradient: autograd through models/gnn.py:54-56 for the
+ * gene-gene / cell-cell loops).  cols % 4 == 0, 16-byte aligned rows. */
+int wsage_rowdot(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int64_t rows, int32_t cols, float* out, void* stream);
 /* out[r,:] = SUM_k slabs[k * slab_stride + r * cols ...] in slab order (the split-K slabs of wsage_dense16 side 1). */
 int wsage_sum_slabs(const float* slabs, int32_t n_slabs, int64_t slab_stride, int64_t rows, int32_t cols,
                     float* out, int64_t ld_out, void* stream);

@@ -207,26 +207,48 @@ split16_transpose_kernel(const float* __restrict__ x, int64_t ld, const int32_t*
     const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
     const int64_t s0 = (int64_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    for (int r = ty; r < 32; r += 8) {
-        const int64_t s = s0 + r;
-        float v = 0.f;
-        if (s < rows && c0 + tx < cols) {
-            const int64_t src = row_ids ? (int64_t)__ldg(row_ids + s) : s;
-            v = __ldg(x + src * ld + c0 + tx) * scale * (rowscale ? __ldg(rowscale + src) : 1.f);
+    // a block owns 32 source rows and walks ALL column tiles (gridDim.y == 1): 317 k blocks of one 32 x 32 tile each were bound
+    // by block scheduling (1.0 ms for 780 k x 400), not by memory
+    for (int c0 = blockIdx.y * 32; c0 < cols; c0 += gridDim.y * 32) {
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t s = s0 + r;
+            float v = 0.f;
+            if (s < rows && c0 + tx < cols) {
+                const int64_t src = row_ids ? (int64_t)__ldg(row_ids + s) : s;
+                v = __ldg(x + src * ld + c0 + tx) * scale * (rowscale ? __ldg(rowscale + src) : 1.f);
+            }
+            tile[r][tx] = v;
         }
-        tile[r][tx] = v;
+        __syncthreads();
+        for (int c = ty; c < 32; c += 8) {
+            const int64_t s = s0 + tx;
+            if (c0 + c < cols && (s < rows || kblocks)) {
+                unsigned short h, l;
+                d16_split(tile[tx][c], fmt, h, l);            // tile is zero past `rows`
+                const int64_t o = kblocks ? ((int64_t)blockIdx.x * ld_o + (c0 + c)) * 32 + tx : (int64_t)(c0 + c) * ld_o + s;
+                hi[o] = h;
+                if (fmt == 0) lo[o] = l;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int c = ty; c < 32; c += 8) {
-        const int64_t s = s0 + tx;
-        if (c0 + c < cols && (s < rows || kblocks)) {
-            unsigned short h, l;
-            d16_split(tile[tx][c], fmt, h, l);            // tile is zero past `rows`
-            const int64_t o = kblocks ? ((int64_t)blockIdx.x * ld_o + (c0 + c)) * 32 + tx : (int64_t)(c0 + c) * ld_o + s;
-            hi[o] = h;
-            if (fmt == 0) lo[o] = l;
+}
+
+// out[r] = <a[r, :], b[r, :]>: warp per row (the self-loop terms of d-alpha: sum_c s_c <h_c, dn_c>)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ b, int64_t ld_b, int64_t rows, int cols,
+              float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    for (int64_t r = warp0; r < rows; r += (int64_t)gridDim.x * 8) {
+        float acc = 0.f;
+        for (int c = lane * 4; c < cols; c += 128) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(a + r * ld_a + c));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(b + r * ld_b + c));
+            acc += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
         }
+        acc = warp_sum(acc);
+        if (lane == 0) out[r] = acc;
     }
 }
 

@@ -198,8 +198,10 @@ int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int6
     unsigned short* l = static_cast<unsigned short*>(lo);
     if (transposed) {
         WSAGE_REQUIRE(rows < ((int64_t)1 << 31) * 32, "too many rows");
-        dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-        split16_transpose_kernel<<<grid, 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_KBLOCKS ? 1 : 0);
+        // few source rows (a weight matrix): spread the column tiles over blocks too; many: one block per 32 rows walks all of them
+        const unsigned gx = (unsigned)((rows + 31) / 32);
+        const unsigned gy = gx >= 4u * kNumSMs ? 1u : (unsigned)((cols + 31) / 32);
+        split16_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_KBLOCKS ? 1 : 0);
         return check_launch("split16_transpose");
     }
     const int64_t cols_p = layout == WSAGE_SPLIT_BLOCKED ? ld_out : (cols + 31) / 32 * 32;
@@ -235,6 +237,15 @@ int wsage_colsum_masked(const float* x, int64_t ld, const float* mask_src, int64
     if (rc != WSAGE_OK) return rc;
     sum_slabs_kernel<<<(cols / 4 + 255) / 256, 256, 0, st>>>(partial, n_partial, cols, 1, cols, out, cols);
     return check_launch("sum_slabs");
+}
+
+int wsage_rowdot(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int64_t rows, int32_t cols, float* out, void* stream) {
+    WSAGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0, "cols must be a positive multiple of 4");
+    if (rows == 0) return WSAGE_OK;
+    WSAGE_REQUIRE(a && b && out && aligned16(a) && aligned16(b), "null or misaligned pointer");
+    WSAGE_REQUIRE(ld_a >= cols && ld_b >= cols && ld_a % 4 == 0 && ld_b % 4 == 0, "bad leading dimension");
+    rowdot_kernel<<<gather_grid(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, ld_a, b, ld_b, rows, cols, out);
+    return check_launch("rowdot");
 }
 
 int wsage_dense16_slots_pad(int32_t gene_slots) { return gene_slots > 0 ? d16_slots_pad(gene_slots) : 0; }

@@ -169,10 +169,12 @@ def _planes_a(x, fmt, mask_src=None):
     return hi, lo, amax, rows, k
 
 
-def _planes_b(x, fmt, k_is_row):
-    """B planes [ceil(K / 32)][ceil16(N)][32] of a matrix whose k index is its row (KBLOCKS) or its column (COLBLOCKS)."""
+def _planes_b(x, fmt, k_is_row, amax=None):
+    """B planes [ceil(K / 32)][ceil16(N)][32] of a matrix whose k index is its row (KBLOCKS) or its column (COLBLOCKS).
+    ``amax``: a device scalar already known to bound |x| (any valid bound gives a valid scale)."""
     rows, cols = x.shape
-    amax = _amax(x, fmt)
+    if amax is None:
+        amax = _amax(x, fmt)
     if k_is_row:
         ld = (cols + 15) // 16 * 16
         hi, lo = _split(x, fmt, _lib.SPLIT_KBLOCKS, ld, ((rows + 31) // 32, ld, 32), amax)
@@ -233,13 +235,13 @@ class _LinearReluD16(torch.autograd.Function):
             n1 = min(n, n0 + _D16_MAX_N)
             _gemm16(a, _planes_b(w[n0:n1], fmt, k_is_row=False), fmt, 0, n1 - n0, y[:, n0:n1],
                     bias=bias[n0:n1].contiguous() if bias is not None else None, relu=relu)
-        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.save_for_backward(x, w, y if relu else None, a[2])
         ctx.relu, ctx.fmt = relu, fmt
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, x_amax = ctx.saved_tensors
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
         dy = dy.contiguous()
         m, n = dy.shape
@@ -259,7 +261,7 @@ class _LinearReluD16(torch.autograd.Function):
             for k0 in range(0, k, _D16_MAX_N):
                 k1 = min(k, k0 + _D16_MAX_N)
                 xs = x if (k0 == 0 and k1 == k) else x[:, k0:k1].contiguous()
-                slabs = _gemm16(g, _planes_b(xs, fmt, k_is_row=True), fmt, 1, k1 - k0, None)
+                slabs = _gemm16(g, _planes_b(xs, fmt, k_is_row=True, amax=x_amax), fmt, 1, k1 - k0, None)
                 _lib.check(lib.wsage_sum_slabs(_ptr(slabs), slabs.shape[0], slabs.shape[1] * slabs.shape[2], n, k1 - k0,
                                                _ptr(dw[:, k0:k1]), dw.stride(0), _stream()), "wsage_sum_slabs")
         if need_b:

@@ -150,10 +150,10 @@ class _LayerAggregate(torch.autograd.Function):
         if need_a:
             da = torch.zeros_like(a)
             da[:g] = dot
-            da[g + 1] = ((hc * dn_c).sum(dim=1) * graph.mean_c).sum()
+            da[g + 1] = (ops.rowdot(hc, dn_c) * graph.mean_c).sum()
             if gene_too:
-                da[:g] += (raw * dn_g).sum(dim=1) * graph.mean_g * graph.norm_g
-                da[g] = ((hg * dn_g).sum(dim=1) * graph.mean_g).sum()
+                da[:g] += ops.rowdot(raw, dn_g) * graph.mean_g * graph.norm_g
+                da[g] = (ops.rowdot(hg, dn_g) * graph.mean_g).sum()
             da = da.reshape(ctx.alpha_shape)
         return dh, da, None, None, None, None, None, None, None
 

@@ -153,6 +153,15 @@ class Csr:
         return int(self.x.shape[0])
 
 
+def rowdot(a, b):
+    """out[r] = <a[r], b[r]> on the device (fp32, warp per row)."""
+    if not (a.is_cuda and a.shape == b.shape and a.shape[1] % 4 == 0 and a.stride(1) == 1 and b.stride(1) == 1):
+        return (a * b).sum(dim=1)
+    out = torch.empty(a.shape[0], device=a.device, dtype=torch.float32)
+    _lib.check(_lib.load().wsage_rowdot(_ptr(a), a.stride(0), _ptr(b), b.stride(0), a.shape[0], a.shape[1], _ptr(out), _stream()), "wsage_rowdot")
+    return out
+
+
 def amax_split16(x, fmt, *, row_ids=None, rowscale=None, layout=_lib.SPLIT_ROWS):
     """(hi, lo, amax, ld): 16-bit planes of x * rowscale * 2^k for wsage_dense16 (k from the amax, device-side), in the
     layout wsage_split16 documents (rows / transposed / 32-column blocks)."""
