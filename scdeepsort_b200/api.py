@@ -40,7 +40,7 @@ def _read_table(path, file_type):
     return pd.read_csv(path, **kw)
 
 
-def _features(x_support: sp.csr_matrix, x_test, gene_feat, dense_dim, seed, device):
+def _features(x_support: sp.csr_matrix, x_test, gene_feat, dense_dim, seed, device, return_graph=False):
     """cat[gene_feat; (X / (rowsum+1e-6)) · gene_feat]  (preprocess_internal.py:186-202; preprocess.py:196-208).  Neither
     the PCA nor the product ever sees a dense [C, G] array: both run as sparse x thin-dense passes of the aggregation
     kernels (features.py).  ``gene_feat`` None: fit the PCA on the support cells."""
@@ -49,7 +49,8 @@ def _features(x_support: sp.csr_matrix, x_test, gene_feat, dense_dim, seed, devi
         gf = pca_gene_features(bg, dense_dim, seed=10086 if seed is None else seed)
     else:
         gf = torch.as_tensor(np.ascontiguousarray(gene_feat), dtype=torch.float32, device=device)
-    return torch.cat([gf, cell_features(bg, gf)], dim=0), gf
+    feats = torch.cat([gf, cell_features(bg, gf)], dim=0)
+    return (feats, gf, bg) if return_graph else (feats, gf)
 
 
 class DeepSortClassifier:
@@ -172,13 +173,13 @@ class DeepSortPredictor:
         xt[:, [gene2id[str(tab.index[i])] for i in known]] = np.where(arr > 0, arr, 0.0)
         xt = xt.tocsr()
         # reference artefacts carry no gene features: PCA on the support cells only (preprocess.py:196)
-        feats, _ = _features(self.support, xt, self.gene_feat, self.dense_dim, 10086, self.device)
+        feats, _, bg = _features(self.support, xt, self.gene_feat, self.dense_dim, 10086, self.device, return_graph=True)
         graph = DeepSortGraph.from_expression(self.support, xt, features=feats.cpu())
         g, ns = graph.num_genes, self.support.shape[0]
         nid = torch.arange(g + ns, g + ns + xt.shape[0])
         runner = Runner(graph, nid, len(self.id2label), dense_dim=self.dense_dim, hidden_dim=self.hidden_dim,
                         n_layers=self.n_layers, batch_size=self.batch_size, unsure_rate=self.unsure_rate,
-                        device=self.device, state_dict=self.state)
+                        device=self.device, state_dict=self.state, bipartite=bg)
         pred, _ = runner.inference()
         names = ['unsure' if p < 0 else self.id2label[p] for p in pred.cpu().tolist()]
         df = pd.DataFrame({'index': list(tab.columns),

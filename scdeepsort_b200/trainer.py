@@ -110,9 +110,13 @@ class Runner:
     """predict.py:17-88 for one test graph: load ``state['model']``, batched inference, labels."""
 
     def __init__(self, graph: DeepSortGraph, test_nid, num_classes: int, *, dense_dim=400, hidden_dim=200,
-                 n_layers=1, batch_size=500, unsure_rate=2.0, device="cuda:0", model_path=None, state_dict=None):
+                 n_layers=1, batch_size=500, unsure_rate=2.0, device="cuda:0", model_path=None, state_dict=None,
+                 bipartite: Optional[BipartiteGraph] = None):
         self.device = torch.device(device)
         self.graph = graph.to(self.device)
+        # the same graph factored for the full-graph form: every test cell is a seed of ONE layer-wise pass instead of
+        # 500-seed NodeFlows that each re-derive the shared lower layers (same logits: tests/test_gpu_c2_parity.py)
+        self.bipartite = bipartite
         self.test_nid = torch.as_tensor(test_nid, dtype=torch.int64)
         self.batch_size, self.unsure_rate, self.n_layers = batch_size, unsure_rate, n_layers
         self.model = GNN(in_feats=dense_dim, n_hidden=hidden_dim, n_classes=num_classes, n_layers=n_layers,
@@ -128,6 +132,10 @@ class Runner:
         """Returns (pred, logits): pred[i] = class index or -1 ('unsure') for test cell i."""
         self.model.eval()
         n = self.graph.number_of_nodes()
+        if self.bipartite is not None:
+            cells = (self.test_nid - self.graph.num_genes).to(self.device)
+            logits = self.model(FullGraphFlow(self.bipartite, self.graph.ndata["features"], seeds=cells))
+            return predict_labels(logits, self.unsure_rate), logits
         new_logits = torch.zeros(n, self.model.linear.out_features, device=self.device)
         for nf in NeighborSampler(g=self.graph, batch_size=self.batch_size, expand_factor=n, num_hops=self.n_layers,
                                   neighbor_type='in', shuffle=False, num_workers=8, seed_nodes=self.test_nid):

@@ -67,3 +67,22 @@ def test_sampled_training_two_layers(tmp_path):
                              gpu_id=0, n_epochs=80, n_layers=2, num_neighbors=12, random_seed=2, learning_rate=5e-3)
     best = clf.fit([(str(tmp_path / "mouse_Demo140_data.csv"), str(tmp_path / "mouse_Demo140_celltype.csv"))])
     assert best["train_acc"] > 0.85
+
+
+def test_runner_full_graph_fast_path_matches_nodeflow_loop(golden_test):
+    """predict.py:61-88 on the reference-built inference graph: the batched NodeFlow loop and the one-pass full-graph
+    form (Runner(bipartite=...), what DeepSortPredictor uses) give the same logits and the same labels."""
+    import scdeepsort_b200 as sd
+    from scdeepsort_b200.trainer import Runner
+    from scds_helpers import golden_csr, golden_graph, golden_state, rel_err
+    z = golden_test
+    gg = golden_graph(z, num_genes=int(z["num_genes"]))
+    g = sd.DeepSortGraph.from_edges(gg.src, gg.dst, gg.weight, gg.node_id, gg.features, gg.num_genes)
+    nid = torch.from_numpy(z["test_nid"])
+    kw = dict(dense_dim=int(z["dense_dim"]), hidden_dim=int(z["hidden"]), n_layers=2, batch_size=16, unsure_rate=2.0,
+              device="cuda:0", state_dict=golden_state(z, "L2"))
+    pred_a, logits_a = Runner(g, nid, int(z["num_labels"]), **kw).inference()
+    bg = sd.BipartiteGraph.from_expression(golden_csr(z), golden_csr(z, "xt"), device="cuda:0").densify(0.1)
+    pred_b, logits_b = Runner(g, nid, int(z["num_labels"]), bipartite=bg, **kw).inference()
+    assert rel_err(logits_a.cpu(), z["L2/logits"]) < 1e-5 and rel_err(logits_b.cpu(), z["L2/logits"]) < 2e-5
+    assert torch.equal(pred_a, pred_b)
