@@ -44,7 +44,8 @@ constexpr int kD16ABytes = kD16TileM * 64;     // 8 KB: one A tile (hi or lo)
 constexpr int kD16BoxMN = 32 * 64;             // 2 KB: one {32, 32} box of the MN-major operands
 constexpr int kD16Threads = 192;
 constexpr int kD16OutCols = 16;                // fp32 columns per TMA store box (64 bytes)
-constexpr int kD16StagingBytes = 4 * 2 * 32 * 64;      // 4 drain warps x 2 buffers x [32 rows][64 B]
+constexpr int kD16BufBytes = 32 * 64;                  // one staging buffer of a drain warp: [32 rows][64 B]
+constexpr int kD16MaxBufs = 6;                         // staging buffers per drain warp (TMA stores in flight)
 constexpr int kD16DefaultChunkRows = 2048;
 constexpr int kD16MaxStages = 6;
 constexpr int kD16SmemBudget = 227 * 1024;
@@ -288,7 +289,17 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
                  ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// waits until at most n of this thread's bulk groups still read their shared-memory source
+__device__ __forceinline__ void bulk_wait_read(int n) {
+    switch (n) {
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -334,6 +345,7 @@ struct D16Params {
     int bf16;
     int n, n_pad, n1, n2;        // output width, rounded up to 16, MMA N halves (n1 <= 256)
     int stages, stage_bytes, tx_bytes, b_bytes;      // stage_bytes: ring pitch (1 KB multiple); tx_bytes: bytes TMA delivers per stage and CTA
+    int nbuf;                    // staging buffers per drain warp
     int m_tiles;                 // destination tiles of 128 (PAIR: an even number of them is processed, the last one may be empty)
     int nb;                      // 32-slot gene blocks per cell tile of the storage
     int ld_hb;                   // rows per k-block of the B planes
@@ -410,7 +422,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     extern __shared__ unsigned char dsmem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* staging = ring + (size_t)p.stages * p.stage_bytes;          // 1024-byte aligned (stage_bytes % 1024 == 0)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kD16StagingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * p.nbuf * kD16BufBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kD16MaxStages;
     uint64_t* tmem_full = bars + 2 * kD16MaxStages;
@@ -583,7 +595,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else {
         // ------------------------------------ drain warps -------------------------------------
         const int q = warp & 3;                                   // TMEM lane quarter of this warp
-        unsigned char* my_stage = staging + (warp - 2) * (2 * 32 * 64);
+        unsigned char* my_stage = staging + (warp - 2) * (p.nbuf * kD16BufBytes);
         const int sw = (lane >> 1) & 3;                           // 64-byte swizzle: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
         const uint32_t tmem_empty_addr = PAIR ? mapa_u32(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
         float h_inv = p.x_amax ? ldexpf(1.f, -d16_scale_exp(*p.x_amax)) : p.x_scale_inv;
@@ -612,8 +624,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int cb = 0; tile_ok && cb * kD16OutCols < p.n_pad; ++cb) {
                     float v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * kD16OutCols), v);
-                    if (cb >= 2) {                                       // the store issued two blocks ago has read this buffer
-                        if (lane == 0) bulk_wait_read_1();
+                    if (cb >= p.nbuf) {                                  // the store issued nbuf blocks ago has read this buffer: the
+                        if (lane == 0) bulk_wait_read(p.nbuf - 1);       // drain is paced by TMA store latency / buffers in flight
                         __syncwarp();
                     }
 #pragma unroll
@@ -642,7 +654,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    unsigned char* buf = my_stage + (cb & 1) * (32 * 64);
+                    unsigned char* buf = my_stage + (cb % p.nbuf) * kD16BufBytes;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ sw) << 4)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
@@ -739,7 +751,7 @@ inline int d16_slots_pad(int gene_slots) { return (gene_slots + 2 * kD16TileM - 
 struct D16Plan {
     bool pair;
     int m_tiles, nb, num_kb, chunk_kb, n_splits, kb_per_split;
-    int n_pad, n1, n2, h1, h2, b_bytes, stage_bytes, tx_bytes, stages;
+    int n_pad, n1, n2, h1, h2, b_bytes, stage_bytes, tx_bytes, stages, nbuf;
     size_t smem_bytes;
 };
 
@@ -795,7 +807,17 @@ inline int d16_plan(const wsage_dense16_args* a, D16Plan& pl) {
     }
     pl.tx_bytes = (terms == 3 ? 2 : 1) * (kD16ABytes + pl.b_bytes);
     pl.stage_bytes = (pl.tx_bytes + 1023) & ~1023;
-    const int fixed = kD16StagingBytes + 256 + 1024;
+    // staging buffers of the drain warps: a drain is paced by (TMA store latency) / (stores in flight), measured 6.8 us per
+    // 128 x 400 tile with two buffers per warp — 10 % of a cell-destination pass at 2048-row chains.  Six buffers when the
+    // ring keeps at least four stages (CTA pairs: 41 KB stages), two otherwise.
+    static const int forced = [] { const char* e = getenv("WSAGE_D16_BUFS"); return e ? atoi(e) : 0; }();
+    pl.nbuf = kD16MaxBufs;
+    if (forced >= 2 && forced <= kD16MaxBufs) pl.nbuf = forced;
+    int fixed = 4 * pl.nbuf * kD16BufBytes + 256 + 1024;
+    if (forced == 0 && (kD16SmemBudget - fixed) / pl.stage_bytes < 4) {
+        pl.nbuf = 2;
+        fixed = 4 * pl.nbuf * kD16BufBytes + 256 + 1024;
+    }
     pl.stages = (kD16SmemBudget - fixed) / pl.stage_bytes;
     if (pl.stages > kD16MaxStages) pl.stages = kD16MaxStages;
     pl.smem_bytes = (size_t)pl.stages * pl.stage_bytes + fixed;
