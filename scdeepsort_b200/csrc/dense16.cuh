@@ -624,8 +624,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int cb = 0; tile_ok && cb * kD16OutCols < p.n_pad; ++cb) {
                     float v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * kD16OutCols), v);
-                    if (cb >= p.nbuf) {                                  // the store issued nbuf blocks ago has read this buffer: the
-                        if (lane == 0) bulk_wait_read(p.nbuf - 1);       // drain is paced by TMA store latency / buffers in flight
+                    if (cb >= p.nbuf) {                                  // the store issued nbuf blocks ago has read this buffer
+                        if (lane == 0) bulk_wait_read(p.nbuf - 1);
                         __syncwarp();
                     }
 #pragma unroll
@@ -807,17 +807,12 @@ inline int d16_plan(const wsage_dense16_args* a, D16Plan& pl) {
     }
     pl.tx_bytes = (terms == 3 ? 2 : 1) * (kD16ABytes + pl.b_bytes);
     pl.stage_bytes = (pl.tx_bytes + 1023) & ~1023;
-    // staging buffers of the drain warps: a drain is paced by (TMA store latency) / (stores in flight), measured 6.8 us per
-    // 128 x 400 tile with two buffers per warp — 10 % of a cell-destination pass at 2048-row chains.  Six buffers when the
-    // ring keeps at least four stages (CTA pairs: 41 KB stages), two otherwise.
+    // staging buffers of the drain warps.  A drain of a 128 x 400 tile costs ~6.8 us (10 % of a cell-destination pass at
+    // 2048-row chains); more TMA stores in flight do not shorten it (WSAGE_D16_BUFS = 2 / 4 / 6: 3.61 / 3.61 / 3.60 ms at c3), so
+    // the default stays at two buffers and the ring keeps its fifth stage.
     static const int forced = [] { const char* e = getenv("WSAGE_D16_BUFS"); return e ? atoi(e) : 0; }();
-    pl.nbuf = kD16MaxBufs;
-    if (forced >= 2 && forced <= kD16MaxBufs) pl.nbuf = forced;
-    int fixed = 4 * pl.nbuf * kD16BufBytes + 256 + 1024;
-    if (forced == 0 && (kD16SmemBudget - fixed) / pl.stage_bytes < 4) {
-        pl.nbuf = 2;
-        fixed = 4 * pl.nbuf * kD16BufBytes + 256 + 1024;
-    }
+    pl.nbuf = (forced >= 2 && forced <= kD16MaxBufs) ? forced : 2;
+    const int fixed = 4 * pl.nbuf * kD16BufBytes + 256 + 1024;
     pl.stages = (kD16SmemBudget - fixed) / pl.stage_bytes;
     if (pl.stages > kD16MaxStages) pl.stages = kD16MaxStages;
     pl.smem_bytes = (size_t)pl.stages * pl.stage_bytes + fixed;
