@@ -326,17 +326,21 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(int n, int bf16, int mn_major
     return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kD16TileM >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// issue only: the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the registers are tied to the wait ("+r"), so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 
 struct D16Params {
@@ -346,6 +350,7 @@ struct D16Params {
     int n, n_pad, n1, n2;        // output width, rounded up to 16, MMA N halves (n1 <= 256)
     int stages, stage_bytes, tx_bytes, b_bytes;      // stage_bytes: ring pitch (1 KB multiple); tx_bytes: bytes TMA delivers per stage and CTA
     int nbuf;                    // staging buffers per drain warp
+    int drain_diag;              // -DWSAGE_TUNING only
     int m_tiles;                 // destination tiles of 128 (PAIR: an even number of them is processed, the last one may be empty)
     int nb;                      // 32-slot gene blocks per cell tile of the storage
     int ld_hb;                   // rows per k-block of the B planes
@@ -621,15 +626,15 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 // the previous chain's adds to these rows have been performed (and the staging buffers are free)
                 if (lane == 0) bulk_wait_all();
                 __syncwarp();
-                for (int cb = 0; tile_ok && cb * kD16OutCols < p.n_pad; ++cb) {
+                // One 16-column block: scale, epilogue terms, swizzled staging, TMA store / reduce-add.
+                auto emit = [&](int cb, const uint32_t (&raw)[16]) {
                     float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * kD16OutCols), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * scale;
                     if (cb >= p.nbuf) {                                  // the store issued nbuf blocks ago has read this buffer
                         if (lane == 0) bulk_wait_read(p.nbuf - 1);
                         __syncwarp();
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] *= scale;
                     if (first && p.selfcoef != nullptr && p.side == 0 && row_ok) {
                         const float* hrow = p.hself + grow * p.ld_hself + cb * kD16OutCols;
 #pragma unroll
@@ -661,9 +666,31 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
+#ifdef WSAGE_TUNING     // drain diagnostics (results wrong): 1 = no TMA at all, 2 = plain stores instead of reduce-adds
+                        if (p.drain_diag == 1) return;
+                        if (p.drain_diag == 2) { tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out); bulk_commit_group(); return; }
+#endif
                         if (first) tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
                         else tma_reduce_add_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
                         bulk_commit_group();
+                    }
+                };
+                // software pipeline over the column blocks: the tcgen05.ld of block cb + 1 is in flight while block cb is staged
+                // and stored (a drain cost ~6.8 us per tile with the load latency exposed in every block)
+                if (tile_ok) {
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
+                    const int n_cb = p.n_pad / kD16OutCols;
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16_issue(t0, ra);
+                    for (int cb = 0; cb < n_cb; cb += 2) {
+                        tmem_ld_wait(ra);
+                        if (cb + 1 < n_cb) tmem_ld16_issue(t0 + (uint32_t)((cb + 1) * kD16OutCols), rb);
+                        emit(cb, ra);
+                        if (cb + 1 < n_cb) {
+                            tmem_ld_wait(rb);
+                            if (cb + 2 < n_cb) tmem_ld16_issue(t0 + (uint32_t)((cb + 2) * kD16OutCols), ra);
+                            emit(cb + 1, rb);
+                        }
                     }
                 }
                 tc_fence_before();

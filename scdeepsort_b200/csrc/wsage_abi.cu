@@ -303,6 +303,9 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
     p.side = a->side; p.terms = bf ? 1 : 3; p.bf16 = bf ? 1 : 0;
     p.n = a->dim; p.n_pad = pl.n_pad; p.n1 = pl.n1; p.n2 = pl.n2;
     p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tx_bytes = pl.tx_bytes; p.b_bytes = pl.b_bytes; p.nbuf = pl.nbuf;
+#ifdef WSAGE_TUNING
+    { static const int dd = [] { const char* e = getenv("WSAGE_D16_DRAIN_DIAG"); return e ? atoi(e) : 0; }(); p.drain_diag = dd; }
+#endif
     p.m_tiles = pl.m_tiles; p.nb = pl.nb; p.num_kb = pl.num_kb; p.chunk_kb = pl.chunk_kb;
     p.n_splits = pl.n_splits; p.kb_per_split = pl.kb_per_split;
     p.amax = bf ? nullptr : a->h_amax;
