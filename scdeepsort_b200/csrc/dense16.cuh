@@ -675,8 +675,11 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         bulk_commit_group();
                     }
                 };
-                // software pipeline over the column blocks: the tcgen05.ld of block cb + 1 is in flight while block cb is staged
-                // and stored (a drain cost ~6.8 us per tile with the load latency exposed in every block)
+                // software pipeline over the column blocks: the tcgen05.ld of block cb + 1 is in flight while block cb is staged and
+                // stored.  (A drain costs ~6.8 us per 128 x 400 tile — 10 % / 5 % of a cell- / gene-destination pass at 2048-row
+                // chains, measured by sweeping the chain length.  Neither this overlap nor more stores in flight shortens it
+                // measurably, and without any TMA traffic it still costs 2/3 of that: what remains is the tensor pipe idling
+                // through the chain hand-over, which only a second accumulator — 800 TMEM columns at N = 400 — would hide.)
                 if (tile_ok) {
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
                     const int n_cb = p.n_pad / kD16OutCols;
