@@ -152,3 +152,52 @@ def test_sharded_math_matches_oracle():
     assert float((logits - logits_full).abs().max() / logits.abs().max()) < 1e-5
     for k, g in grads.items():
         assert float((grads_full[k] - g).abs().max() / g.abs().max().clamp(min=1e-30)) < 1e-4, k
+
+
+def _dropout_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sd.ops.spmm = _spmm_cpu
+        torch.manual_seed(100 + rank)                      # the ranks' default generators differ, as in real runs
+        lo, hi = parallel.cell_ranges(C, world)[rank]
+        bg = synthetic_bipartite(C, G, DEG, device="cpu", cell_range=(lo, hi))
+        parallel.globalize_gene_normalisers(bg)
+        feats = synthetic_features(bg, D0)
+        m = sd.GNN(D0, H, K, 2, G, activation=torch.relu, dropout=0.3)
+        parallel.broadcast_params(m)
+        m.train()
+        seen = []
+        real = sd.gnn._LayerAggregate.apply
+
+        def spy(h, alpha, graph, algo, gene_too, ready, gmask, cmask, sharded):
+            seen.append((gmask.clone(), cmask.clone()))
+            return real(h, alpha, graph, algo, gene_too, ready, gmask, cmask, sharded)
+
+        sd.gnn._LayerAggregate.apply = spy
+        logits = parallel.sharded_forward(m, bg, feats)
+        q.put((rank, [g.numpy() for g, _ in seen], [c.numpy() for _, c in seen], logits.detach().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_dropout_uses_one_mask_for_the_replicated_gene_rows():
+    """the gene rows are replicated state — under dropout every rank must drop the SAME gene entries (a shared
+    generator), while the cell rows of each shard get their own masks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dropout_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    (_, g0, c0, _), (_, g1, c1, _) = res
+    assert len(g0) == 2
+    for a, b in zip(g0, g1):
+        assert a.shape == (G, a.shape[1]) and np.array_equal(a, b)           # same gene mask on both ranks
+        assert 0.2 < float((a == 0).mean()) < 0.4 and np.allclose(a[a != 0], 1 / 0.7)
+    assert not np.array_equal(g0[0], g0[1])                                   # a fresh mask per layer
+    assert c0[0].shape != c1[0].shape or not np.array_equal(c0[0], c1[0])    # cell masks are per shard
