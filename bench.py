@@ -384,6 +384,8 @@ def run_ours(a):
                             "sample": f"first {n2} cells, same step without the per-edge message tensor: torch sparse-CSR x "
                                       f"dense products (oracle/spmm_oracle.py), 1 warm-up + 1 timed step"}
 
+    if trainer.peer_group is not None:
+        trainer.peer_group.check()              # a timed-out cross-GPU barrier is an error, not a slow step
     if rank == 0:
         print(json.dumps({
             "metric": "cells/sec (forward+backward)", "value": a.cells / (ms_step / 1e3), "unit": "cells/s",
@@ -393,12 +395,17 @@ def run_ours(a):
                        "dense_threshold": a.dense_threshold, "dense_fmt": a.dense_fmt, "dense_genes": int(len(getattr(graph, "dense_genes", []))),
                        "csr_entries_left": graph.cell_csr.nnz, "dropout": a.dropout,
                        "parallelism": f"cell-sharded x{world}" if world > 1 else "single GPU",
+                       "gene_sum_exchange": None if world == 1 else "wsage_peer_reduce (slab sum + all-reduce + epilogue, one kernel over "
+                       "NVLink peer memory)" if trainer.peer_group is not None else "sum_slabs + NCCL all-reduce + element-wise",
                        "l2_policy": "inputs_exceed_l2 (graph + activations >> 126 MB; no explicit flush)",
                        "graph_build_s": build_s, "final_loss_per_cell": final_loss / (hi - lo)},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
         }))
     if world > 1:
+        if trainer.peer_group is not None:
+            from scdeepsort_b200 import peer
+            peer.disable()
         dist.destroy_process_group()
 
 

@@ -290,6 +290,55 @@ int wsage_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
                     void* stream);   /* hyper-parameters in double: 1-beta and lr/(1-beta1^step) are formed in fp64 as torch does */
 
+/* ---------------------------------------------------------------------------------------
+ * Exchange step of the cell-sharded full-graph pass over NVLink peer memory (one process per GPU, one node).
+ *
+ * The gene destinations of /root/reference/models/gnn.py:65 (`fn.mean` over ALL in-edges) receive messages from every
+ * rank's cell shard: the per-rank sums of wsage_dense16 (side 1) must be added over the ranks.  wsage_peer_reduce
+ * does the local split-K reduction, that sum (reduce-scatter + all-gather by peer loads, rank order, every rank
+ * gets identical bits) and the epilogue  out = dscale * raw + selfcoef * hself  in ONE kernel; the reference has no
+ * counterpart (single process), the NCCL form is  sum_slabs -> ncclAllReduce -> two element-wise kernels.
+ *
+ * Set-up, once per process: wsage_peer_alloc (device memory of wsage_peer_bytes(max_elems), zeroed, plus its 64-byte
+ * cudaIpc handle), handles exchanged by the host (torch.distributed / MPI / files), wsage_peer_open on the others'.
+ * Every rank then calls wsage_peer_reduce in the same order with the same rows / dim and epoch = 1, 3, 5, ...
+ * A barrier that does not complete within timeout_s marks the allocation failed (wsage_peer_status != 0) and the
+ * kernel returns: nothing hangs, the host raises.
+ * ------------------------------------------------------------------------------------- */
+#define WSAGE_PEER_MAX 8
+size_t wsage_peer_bytes(int64_t max_elems);
+int wsage_peer_alloc(int64_t max_elems, void** base, void* ipc_handle64);
+int wsage_peer_open(const void* ipc_handle64, void** base);
+int wsage_peer_close(void* base);                /* a base from wsage_peer_open  */
+int wsage_peer_free(void* base);                 /* a base from wsage_peer_alloc */
+int wsage_peer_status(const void* base, int32_t* status);   /* synchronises the device */
+
+typedef struct wsage_peer_reduce_args {
+    int32_t        rank;
+    int32_t        world;        /* <= WSAGE_PEER_MAX                                                    */
+    void* const*   bases;        /* host array of `world` allocation bases in rank order (own: from alloc) */
+    int64_t        max_elems;    /* what the allocations were sized for, rows * dim <= max_elems         */
+    uint32_t       epoch;        /* 1, 3, 5, ... identical on every rank                                 */
+    const float*   slabs;        /* [n_slabs][slab_rows][dim] partial sums of this rank                  */
+    int32_t        n_slabs;
+    int64_t        slab_rows;
+    const int32_t* slot_of_row;  /* slab row of output row r, or NULL for r                              */
+    int64_t        rows;
+    int32_t        dim;          /* % 4 == 0                                                             */
+    const float*   dscale;       /* optional, per row                                                    */
+    const float*   selfcoef;     /* optional, per row (then hself)                                       */
+    const float*   hself;
+    int64_t        ld_hself;
+    float*         out;          /* [rows][ld_out] or NULL                                               */
+    int64_t        ld_out;
+    float*         raw;          /* [rows][ld_raw] the sum itself, or NULL                               */
+    int64_t        ld_raw;
+    float          timeout_s;    /* 0 = default (10 s)                                                   */
+    int32_t        grid;         /* CTAs, 0 = one per SM: all must be resident, and every call on an allocation uses the same value */
+} wsage_peer_reduce_args;
+
+int wsage_peer_reduce(const wsage_peer_reduce_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

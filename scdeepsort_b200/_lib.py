@@ -23,7 +23,10 @@ EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_blo
            "wsage_split16_masked", "wsage_sum_slabs", "wsage_colsum_masked", "wsage_rowdot",
            "wsage_dense16_slots_pad", "wsage_dense16_splits", "wsage_dense16",
            "wsage_split_tf32", "wsage_linear_tc", "wsage_grad_w_splits", "wsage_grad_w_tc", "wsage_sample_neighbors",
-           "wsage_softmax_ce", "wsage_adam_step")
+           "wsage_softmax_ce", "wsage_adam_step",
+           "wsage_peer_bytes", "wsage_peer_alloc", "wsage_peer_open", "wsage_peer_close", "wsage_peer_free", "wsage_peer_status",
+           "wsage_peer_reduce")
+PEER_MAX = 8
 
 
 class SpmmArgs(Structure):
@@ -48,6 +51,16 @@ class Dense16Args(Structure):
         ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
         ("out", c_void_p), ("ld_out", c_int64), ("chunk_rows", c_int32),
         ("x_amax", c_void_p), ("bias", c_void_p), ("relu", c_int32),
+    ]
+
+
+class PeerReduceArgs(Structure):
+    """Mirror of ``wsage_peer_reduce_args`` (include/wsage.h)."""
+    _fields_ = [
+        ("rank", c_int32), ("world", c_int32), ("bases", POINTER(c_void_p)), ("max_elems", c_int64), ("epoch", ctypes.c_uint32),
+        ("slabs", c_void_p), ("n_slabs", c_int32), ("slab_rows", c_int64), ("slot_of_row", c_void_p), ("rows", c_int64),
+        ("dim", c_int32), ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
+        ("out", c_void_p), ("ld_out", c_int64), ("raw", c_void_p), ("ld_raw", c_int64), ("timeout_s", c_float), ("grid", c_int32),
     ]
 
 
@@ -129,6 +142,20 @@ def load():
     lib.wsage_adam_step.restype = c_int32
     lib.wsage_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int32, c_void_p]
+    lib.wsage_peer_bytes.restype = c_size_t
+    lib.wsage_peer_bytes.argtypes = [c_int64]
+    lib.wsage_peer_alloc.restype = c_int32
+    lib.wsage_peer_alloc.argtypes = [c_int64, POINTER(c_void_p), c_void_p]
+    lib.wsage_peer_open.restype = c_int32
+    lib.wsage_peer_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.wsage_peer_close.restype = c_int32
+    lib.wsage_peer_close.argtypes = [c_void_p]
+    lib.wsage_peer_free.restype = c_int32
+    lib.wsage_peer_free.argtypes = [c_void_p]
+    lib.wsage_peer_status.restype = c_int32
+    lib.wsage_peer_status.argtypes = [c_void_p, POINTER(c_int32)]
+    lib.wsage_peer_reduce.restype = c_int32
+    lib.wsage_peer_reduce.argtypes = [POINTER(PeerReduceArgs), c_void_p]
     _lib = lib
     return lib
 

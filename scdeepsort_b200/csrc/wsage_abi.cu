@@ -5,13 +5,14 @@
 #include "dense16.cuh"
 #include "sampler.cuh"
 #include "loss_adam.cuh"
+#include "peer_reduce.cuh"
 #include <math.h>
 
 using namespace wsage;
 
 extern "C" {
 
-int wsage_version(void) { return 2000; }
+int wsage_version(void) { return 2001; }
 
 const char* wsage_last_error(void) { return g_err; }
 
@@ -246,6 +247,98 @@ int wsage_rowdot(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int
     WSAGE_REQUIRE(ld_a >= cols && ld_b >= cols && ld_a % 4 == 0 && ld_b % 4 == 0, "bad leading dimension");
     rowdot_kernel<<<gather_grid(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, ld_a, b, ld_b, rows, cols, out);
     return check_launch("rowdot");
+}
+
+// ---- exchange step over peer memory (peer_reduce.cuh) ----
+static size_t peer_set_bytes(int64_t max_elems) { return ((size_t)max_elems * sizeof(float) + 255) / 256 * 256; }
+
+size_t wsage_peer_bytes(int64_t max_elems) { return max_elems > 0 ? kPeerHeaderBytes + 4 * peer_set_bytes(max_elems) : 0; }
+
+#define WSAGE_CUDA(call, what)                                                                     \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e_));                \
+            cudaGetLastError();                                                                    \
+            return WSAGE_ECUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+int wsage_peer_alloc(int64_t max_elems, void** base, void* ipc_handle64) {
+    WSAGE_REQUIRE(max_elems > 0 && base && ipc_handle64, "max_elems must be positive, base and handle non-null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the handle as 64 bytes");
+    void* p = nullptr;
+    const size_t bytes = wsage_peer_bytes(max_elems);
+    WSAGE_CUDA(cudaMalloc(&p, bytes), "cudaMalloc (peer buffer)");
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(ipc_handle64), p);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "peer buffer set-up: %s", cudaGetErrorString(e));
+        cudaFree(p);
+        cudaGetLastError();
+        return WSAGE_ECUDA;
+    }
+    *base = p;
+    return WSAGE_OK;
+}
+
+int wsage_peer_open(const void* ipc_handle64, void** base) {
+    WSAGE_REQUIRE(ipc_handle64 && base, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, sizeof(h));
+    WSAGE_CUDA(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return WSAGE_OK;
+}
+
+int wsage_peer_close(void* base) {
+    if (base) WSAGE_CUDA(cudaIpcCloseMemHandle(base), "cudaIpcCloseMemHandle");
+    return WSAGE_OK;
+}
+
+int wsage_peer_free(void* base) {
+    if (base) WSAGE_CUDA(cudaFree(base), "cudaFree (peer buffer)");
+    return WSAGE_OK;
+}
+
+int wsage_peer_status(const void* base, int32_t* status) {
+    WSAGE_REQUIRE(base && status, "null argument");
+    WSAGE_CUDA(cudaMemcpy(status, static_cast<const unsigned char*>(base) + kPeerStatusOff, sizeof(int32_t), cudaMemcpyDeviceToHost),
+               "cudaMemcpy (peer status)");
+    return WSAGE_OK;
+}
+
+int wsage_peer_reduce(const wsage_peer_reduce_args* a, void* stream) {
+    WSAGE_REQUIRE(a != nullptr, "null args");
+    WSAGE_REQUIRE(a->world >= 1 && a->world <= kPeerMax && a->rank >= 0 && a->rank < a->world, "rank / world out of range");
+    WSAGE_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim % 4 == 0 && a->rows * a->dim <= a->max_elems, "rows * dim must fit max_elems, dim % 4 == 0");
+    WSAGE_REQUIRE(a->epoch >= 1 && a->epoch % 2 == 1 && a->epoch < 0xfffffff0u / kNumSMs, "epoch must be odd: 1, 3, 5, ...");
+    WSAGE_REQUIRE(a->grid >= 0 && a->grid <= 2 * kNumSMs, "grid must be 0 (one CTA per SM) or at most two CTAs per SM");
+    WSAGE_REQUIRE(a->bases && a->slabs && aligned16(a->slabs) && a->n_slabs >= 1 && a->slab_rows >= 1, "null bases / slabs");
+    WSAGE_REQUIRE(a->slot_of_row || a->slab_rows >= a->rows, "slab_rows < rows without a row map");
+    WSAGE_REQUIRE(a->out || a->raw, "neither out nor raw");
+    WSAGE_REQUIRE(!a->out || (aligned16(a->out) && a->ld_out >= a->dim && a->ld_out % 4 == 0), "bad out");
+    WSAGE_REQUIRE(!a->raw || (aligned16(a->raw) && a->ld_raw >= a->dim && a->ld_raw % 4 == 0), "bad raw");
+    WSAGE_REQUIRE(!a->selfcoef || (a->hself && aligned16(a->hself) && a->ld_hself >= a->dim && a->ld_hself % 4 == 0), "selfcoef needs hself");
+    PeerReduceParams p{};
+    p.rank = a->rank; p.world = a->world;
+    const size_t set = peer_set_bytes(a->max_elems);
+    const int parity = (int)((a->epoch >> 1) & 1u);
+    for (int r = 0; r < a->world; ++r) {
+        WSAGE_REQUIRE(a->bases[r] != nullptr, "null peer base");
+        unsigned char* b = static_cast<unsigned char*>(a->bases[r]);
+        p.header[r] = b;
+        p.partial[r] = reinterpret_cast<float*>(b + kPeerHeaderBytes + (size_t)parity * set);
+        p.result[r] = reinterpret_cast<float*>(b + kPeerHeaderBytes + (size_t)(2 + parity) * set);
+    }
+    p.slabs = a->slabs; p.n_slabs = a->n_slabs; p.slab_rows = a->slab_rows; p.slot_of_row = a->slot_of_row;
+    p.rows = a->rows; p.dim = a->dim; p.epoch = a->epoch;
+    p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
+    p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
+    p.timeout_ns = (unsigned long long)((a->timeout_s > 0.f ? a->timeout_s : 10.f) * 1e9);
+    // one CTA per SM, all resident: the barriers inside spin on a grid-wide counter
+    peer_reduce_kernel<<<a->grid > 0 ? a->grid : kNumSMs, kPeerThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("peer_reduce");
 }
 
 int wsage_dense16_slots_pad(int32_t gene_slots) { return gene_slots > 0 ? d16_slots_pad(gene_slots) : 0; }

@@ -94,7 +94,17 @@ class _LayerAggregate(torch.autograd.Function):
         if gene_too:
             need_raw = ctx.needs_input_grad[1]
             dscale_g = graph.mean_g * graph.norm_g * a[:g]
-            if sharded:
+            pg = getattr(graph, "peer_group", None) if sharded else None        # parallel.enable_peer_exchange
+            if pg is not None and g * h.shape[1] > pg.max_elems:
+                raise RuntimeError(f"the peer exchange buffers hold {pg.max_elems} values, this layer needs {g * h.shape[1]}")
+            if pg is not None:
+                # split-K slabs of this shard -> sum over the ranks -> scale + self loop: one kernel over peer memory
+                d = graph.gene_csr.dense
+                slabs = ops.dense16(d, 1, hc[:ns], n_src_cells=ns)
+                raw = torch.empty(g, h.shape[1], device=h.device, dtype=torch.float32) if need_raw else None
+                pg.reduce(slabs, g, slot_of_row=d.slot_of_gene, dscale=dscale_g, selfcoef=graph.mean_g * a[g], hself=hg,
+                          out=neigh[:g], raw=raw)
+            elif sharded:
                 _, raw, _ = ops.spmm(graph.gene_csr, hc[:ns], want_out=False, want_raw=True, algo=algo)
                 _all_reduce_(raw)
                 torch.mul(raw, dscale_g[:, None], out=neigh[:g])

@@ -79,6 +79,22 @@ def sharded_forward(model: GNN, graph: BipartiteGraph, features: torch.Tensor, c
     return model._forward_full(flow)
 
 
+def enable_peer_exchange(graph: BipartiteGraph, max_dim: int):
+    """Collective.  Routes the all-reduce of the raw gene sums of ``graph`` through ``wsage_peer_reduce`` (one kernel over
+    NVLink peer memory, scdeepsort_b200/peer.py) when every rank runs its gene passes entirely on the dense block and the
+    GPUs can map each other's memory; otherwise the NCCL all-reduce stays.  Sets and returns ``graph.peer_group``."""
+    from . import peer
+    graph.peer_group = None
+    if not is_dist() or graph.device.type != "cuda":
+        return None
+    mine = graph.gene_csr.dense is not None and graph.gene_csr.dense_side == 1 and graph.gene_csr.nnz == 0
+    flag = torch.tensor([1 if mine else 0], device=graph.device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag) == 1:
+        graph.peer_group = peer.enable(graph.num_genes * int(max_dim))
+    return graph.peer_group
+
+
 def allreduce_grads(model: torch.nn.Module):
     """One flattened all-reduce(sum) of every parameter gradient (≈1.4 MB at H=400)."""
     if not is_dist():

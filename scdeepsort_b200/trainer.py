@@ -164,6 +164,10 @@ class FullGraphTrainer:
         self.model.spmm_algo = spmm_algo
         self.optimizer = Adam(self.model.parameters(), lr=lr, weight_decay=weight_decay)
         self.sharded = sharded
+        self.peer_group = None
+        if sharded:
+            from .parallel import enable_peer_exchange
+            self.peer_group = enable_peer_exchange(graph, max(dense_dim, hidden_dim))
         self._dev_feat = self._dev_lab = None
         self._copy_stream = None
 

@@ -34,6 +34,9 @@ def test_spmm_args_struct_layout_matches_header():
     body = header[header.index("typedef struct wsage_dense16_args {"):header.index("} wsage_dense16_args;")]
     names = re.findall(r"\b([a-z_]+);", body)
     assert names == [f[0] for f in sd._lib.Dense16Args._fields_]
+    body = header[header.index("typedef struct wsage_peer_reduce_args {"):header.index("} wsage_peer_reduce_args;")]
+    names = re.findall(r"\b([a-z_]+);", body)
+    assert names == [f[0] for f in sd._lib.PeerReduceArgs._fields_]
 
 
 def test_argument_errors_are_reported_not_thrown():
@@ -366,3 +369,21 @@ def test_densify_with_test_cells_splits_all_three_csrs():
     assert sup.n_dst == cs and sup.dense is bg.cell_csr.dense and sup.nnz == int(bg.cell_csr.rowptr[cs])
     np.testing.assert_allclose(_csr_matrix(sup) + csr_dense_matrix(sup).numpy(), xs.toarray(), **tol)
     assert bg.support_cell_csr() is sup
+
+
+def test_peer_reduce_rejects_bad_arguments_before_touching_the_device():
+    """ABI 2001: wsage_peer_reduce validates on the host (no GPU here: every call must fail with EINVAL, not crash)."""
+    import ctypes
+    lib = sd._lib.load()
+    assert lib.wsage_version() >= 2001
+    assert lib.wsage_peer_bytes(0) == 0 and lib.wsage_peer_bytes(1000) == 4096 + 4 * 4096
+    a = sd._lib.PeerReduceArgs()
+    assert lib.wsage_peer_reduce(None, None) == sd._lib.EINVAL
+    a.rank, a.world = 0, 9
+    assert lib.wsage_peer_reduce(ctypes.byref(a), None) == sd._lib.EINVAL and b"world" in lib.wsage_last_error()
+    a.world, a.rows, a.dim, a.max_elems, a.epoch = 2, 10, 6, 100, 1
+    assert lib.wsage_peer_reduce(ctypes.byref(a), None) == sd._lib.EINVAL and b"dim % 4" in lib.wsage_last_error()
+    a.dim, a.epoch = 8, 2
+    assert lib.wsage_peer_reduce(ctypes.byref(a), None) == sd._lib.EINVAL and b"epoch" in lib.wsage_last_error()
+    a.epoch = 3
+    assert lib.wsage_peer_reduce(ctypes.byref(a), None) == sd._lib.EINVAL and b"null" in lib.wsage_last_error()
