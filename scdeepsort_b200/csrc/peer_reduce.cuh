@@ -24,7 +24,7 @@
 namespace wsage {
 
 constexpr int kPeerMax = 8;
-constexpr int kPeerThreads = 256;     // two such CTAs fit an SM: two ranks' kernels can share one device (tests)
+constexpr int kPeerThreads = 512;     // at most 64 registers: two CTAs per SM, the bandwidth phases need the occupancy
 // layout of the header at the start of every rank's peer allocation (bytes)
 constexpr int kPeerFlagsOff = 0;        // unsigned flags[kPeerMax]: flags[r] written by rank r
 constexpr int kPeerArriveOff = 256;     // unsigned: CTAs of the local grid that reached the barrier (monotonic)
@@ -151,17 +151,25 @@ __global__ void __launch_bounds__(kPeerThreads, 2) peer_reduce_kernel(const __gr
     {
         float4* dst = reinterpret_cast<float4*>(p.partial[p.rank]);
         const int64_t slab_stride = p.slab_rows * p.dim;
-        for (int64_t i = tid; i < p.rows * q4; i += nthreads) {
-            const int64_t r = i / q4;
-            const int c4 = (int)(i - r * q4);
-            const int64_t slot = p.slot_of_row ? __ldg(p.slot_of_row + r) : r;
-            const float* src = p.slabs + slot * p.dim + c4 * 4;
-            float4 acc = __ldg(reinterpret_cast<const float4*>(src));
+        const int64_t total = p.rows * q4;
+        for (int64_t i0 = tid; i0 < total; i0 += 2 * nthreads) {          // two independent chains per thread
+            const int64_t i1 = i0 + nthreads;
+            const bool two = i1 < total;
+            const int64_t r0 = i0 / q4, r1 = two ? i1 / q4 : r0;
+            const int64_t s0 = p.slot_of_row ? __ldg(p.slot_of_row + r0) : r0;
+            const int64_t s1 = p.slot_of_row ? __ldg(p.slot_of_row + r1) : r1;
+            const float* a0 = p.slabs + s0 * p.dim + (i0 - r0 * q4) * 4;
+            const float* a1 = p.slabs + s1 * p.dim + ((two ? i1 : i0) - r1 * q4) * 4;
+            float4 x = __ldg(reinterpret_cast<const float4*>(a0));
+            float4 y = __ldg(reinterpret_cast<const float4*>(a1));
             for (int s = 1; s < p.n_slabs; ++s) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + s * slab_stride));
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                const float4 u = __ldg(reinterpret_cast<const float4*>(a0 + s * slab_stride));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a1 + s * slab_stride));
+                x.x += u.x; x.y += u.y; x.z += u.z; x.w += u.w;
+                y.x += v.x; y.y += v.y; y.z += v.z; y.w += v.w;
             }
-            dst[i] = acc;
+            dst[i0] = x;
+            if (two) dst[i1] = y;
         }
     }
     if (!peer_barrier(p, p.epoch, t_start)) return;
@@ -171,14 +179,16 @@ __global__ void __launch_bounds__(kPeerThreads, 2) peer_reduce_kernel(const __gr
     {
         float4* res = reinterpret_cast<float4*>(p.result[p.rank]);
         for (int64_t i = r_lo * q4 + tid; i < r_hi * q4; i += nthreads) {
-            float4 v[kPeerMax];
+            float4 acc = ld_peer_f4(p.partial[0] + i * 4);
+            for (int k0 = 1; k0 < p.world; k0 += 4) {                      // up to four peer loads in flight, added in rank order
+                float4 v[4];
 #pragma unroll
-            for (int k = 0; k < kPeerMax; ++k)
-                if (k < p.world) v[k] = ld_peer_f4(p.partial[k] + i * 4);
-            float4 acc = v[0];
+                for (int k = 0; k < 4; ++k)
+                    if (k0 + k < p.world) v[k] = ld_peer_f4(p.partial[k0 + k] + i * 4);
 #pragma unroll
-            for (int k = 1; k < kPeerMax; ++k)
-                if (k < p.world) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+                for (int k = 0; k < 4; ++k)
+                    if (k0 + k < p.world) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+            }
             res[i] = acc;
             const int64_t r = i / q4;
             peer_emit(p, r, (int)(i - r * q4), acc);

@@ -312,8 +312,8 @@ int wsage_peer_reduce(const wsage_peer_reduce_args* a, void* stream) {
     WSAGE_REQUIRE(a != nullptr, "null args");
     WSAGE_REQUIRE(a->world >= 1 && a->world <= kPeerMax && a->rank >= 0 && a->rank < a->world, "rank / world out of range");
     WSAGE_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim % 4 == 0 && a->rows * a->dim <= a->max_elems, "rows * dim must fit max_elems, dim % 4 == 0");
-    WSAGE_REQUIRE(a->epoch >= 1 && a->epoch % 2 == 1 && a->epoch < 0xfffffff0u / kNumSMs, "epoch must be odd: 1, 3, 5, ...");
-    WSAGE_REQUIRE(a->grid >= 0 && a->grid <= 2 * kNumSMs, "grid must be 0 (one CTA per SM) or at most two CTAs per SM");
+    WSAGE_REQUIRE(a->epoch >= 1 && a->epoch % 2 == 1 && a->epoch < 0xfffffff0u / (2 * kNumSMs), "epoch must be odd: 1, 3, 5, ...");
+    WSAGE_REQUIRE(a->grid >= 0 && a->grid <= 2 * kNumSMs, "grid must be 0 (two CTAs per SM) or at most two CTAs per SM");
     WSAGE_REQUIRE(a->bases && a->slabs && aligned16(a->slabs) && a->n_slabs >= 1 && a->slab_rows >= 1, "null bases / slabs");
     WSAGE_REQUIRE(a->slot_of_row || a->slab_rows >= a->rows, "slab_rows < rows without a row map");
     WSAGE_REQUIRE(a->out || a->raw, "neither out nor raw");
@@ -336,8 +336,8 @@ int wsage_peer_reduce(const wsage_peer_reduce_args* a, void* stream) {
     p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
     p.timeout_ns = (unsigned long long)((a->timeout_s > 0.f ? a->timeout_s : 10.f) * 1e9);
-    // one CTA per SM, all resident: the barriers inside spin on a grid-wide counter
-    peer_reduce_kernel<<<a->grid > 0 ? a->grid : kNumSMs, kPeerThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    // two CTAs per SM, all resident: the barriers inside spin on a grid-wide counter
+    peer_reduce_kernel<<<a->grid > 0 ? a->grid : 2 * kNumSMs, kPeerThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("peer_reduce");
 }
 

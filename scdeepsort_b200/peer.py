@@ -78,7 +78,7 @@ class PeerGroup:
         streams): exercises the exchange without a second GPU.  All the ranks' CTAs must be resident together (two
         per SM fit), so each rank gets its share of the device."""
         allocs = [cls._alloc(max_elems)[0] for _ in range(world)]
-        grid = 0 if world == 1 else 148 if world == 2 else 256 // world
+        grid = 0 if world == 1 else 296 // world
         return [cls(r, world, max_elems, allocs, allocs[r], [], timeout_s, grid) for r in range(world)]
 
     # ---- the exchange ----

@@ -213,7 +213,7 @@ class FullGraphTrainer:
             from .parallel import allreduce_grads
             allreduce_grads(self.model)
         self.optimizer.step()
-        return float(loss) if return_loss else loss.detach()
+        return float(loss.detach()) if return_loss else loss.detach()
 
     @torch.no_grad()
     def predict(self, features, unsure_rate=2.0):
