@@ -219,6 +219,10 @@ typedef struct wsage_dense16_args {
     const float*   x_amax;       /* device scalar the X planes were scaled by (then x_scale is ignored), or NULL */
     const float*   bias;         /* side 0: [dim] added to every row, or NULL                            */
     int32_t        relu;         /* side 0: max(., 0); needs the k range to fit one chain                */
+    /* ABI >= 2001.  Side 0 cuts the tiles of the last, partial round of destination tiles along k and lets the pieces
+     * reduce-add in arrival order (fp32 sums of those rows may differ in the last bit from run to run); 1 keeps every
+     * tile whole: bitwise reproducible, up to one tile time slower per call. */
+    int32_t        deterministic;
 } wsage_dense16_args;
 
 int wsage_dense16_slots_pad(int32_t gene_slots);

@@ -50,7 +50,7 @@ class Dense16Args(Structure):
         ("h_amax", c_void_p), ("dim", c_int32), ("n_dst", c_int64), ("n_src_cells", c_int64),
         ("dscale", c_void_p), ("selfcoef", c_void_p), ("hself", c_void_p), ("ld_hself", c_int64),
         ("out", c_void_p), ("ld_out", c_int64), ("chunk_rows", c_int32),
-        ("x_amax", c_void_p), ("bias", c_void_p), ("relu", c_int32),
+        ("x_amax", c_void_p), ("bias", c_void_p), ("relu", c_int32), ("deterministic", c_int32),
     ]
 
 

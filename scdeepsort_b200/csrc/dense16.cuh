@@ -370,6 +370,10 @@ struct D16Params {
     int ld_hb;                   // rows per k-block of the B planes
     int num_kb, chunk_kb;        // k-blocks in all / per accumulation chain
     int n_splits, kb_per_split;  // side 0: 1, num_kb
+    // side 0, last (partial) round of destination tiles: its tail_tiles tiles are cut along k into tail_splits items of tail_kb
+    // k-blocks each, which reduce-add into rows the host zeroed — the round then costs 1 / tail_splits of a tile.  Items below
+    // full_items are decoded the plain way (all items when there is no tail).
+    int full_items, tail_tiles, tail_splits, tail_kb;
     int64_t rows_per_split;      // side 1: rows of the output map per split (padded slots)
     int64_t m_total;             // destination rows
     const float* amax;           // device scalar the per-pass operand was scaled by, or null
@@ -382,6 +386,27 @@ struct D16Params {
     const float* hself;
     int64_t ld_hself;
 };
+
+struct D16Item {
+    int m;            // destination tile (pair of tiles) of the item
+    int split;        // side 1: slab
+    int kb0, kb1;     // k-blocks
+    bool add_only;    // the destination rows were zeroed by the host: every chain reduce-adds
+};
+__device__ __forceinline__ D16Item d16_item(const D16Params& p, int item, int m_items) {
+    D16Item w;
+    if (item < p.full_items) {
+        w.m = item % m_items; w.split = item / m_items;
+        w.kb0 = w.split * p.kb_per_split; w.kb1 = min(p.num_kb, w.kb0 + p.kb_per_split);
+        w.add_only = false;
+    } else {
+        const int j = item - p.full_items;
+        w.m = p.full_items + j % p.tail_tiles; w.split = 0;
+        w.kb0 = (j / p.tail_tiles) * p.tail_kb; w.kb1 = min(p.num_kb, w.kb0 + p.tail_kb);
+        w.add_only = true;
+    }
+    return w;
+}
 
 // ---- CTA-pair (cta_group::2) variants of the TMA / MMA / commit instructions -------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -455,7 +480,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int n_groups = PAIR ? gridDim.x >> 1 : gridDim.x;
     const int tiles_per_item = PAIR ? 2 : 1;
     const int m_items = (p.m_tiles + tiles_per_item - 1) / tiles_per_item;     // destination tiles (pairs of tiles) per split
-    const int n_items = m_items * p.n_splits;
+    const int n_items = p.full_items + p.tail_tiles * p.tail_splits;
     const int a_planes = p.terms == 3 ? 2 : 1;
     // rows of B (= output columns) this CTA stages for the two MMA column groups
     const int h1 = PAIR ? p.n1 / 2 : p.n1, h2 = PAIR ? p.n2 / 2 : p.n2;
@@ -488,8 +513,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
             int it = 0;
             for (int item = group; item < n_items; item += n_groups) {
-                const int mt = (item % m_items) * tiles_per_item + rank, split = item / m_items;
-                const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                const D16Item w = d16_item(p, item, m_items);
+                const int mt = w.m * tiles_per_item + rank, kb0 = w.kb0, kb1 = w.kb1;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
@@ -556,8 +581,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint64_t n2_off = (uint64_t)((h1 * 64) >> 4);
             int it = 0, chunk_no = 0;
             for (int item = group; item < n_items; item += n_groups) {
-                const int split = item / m_items;
-                const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                const D16Item w = d16_item(p, item, m_items);
+                const int kb0 = w.kb0, kb1 = w.kb1;
                 for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb, ++chunk_no) {
                     const int c1 = min(kb1, c0 + p.chunk_kb);
                     mbar_wait(tmem_empty, (chunk_no & 1) ^ 1);             // the drain warps (of both CTAs) have emptied the accumulators
@@ -622,8 +647,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint64_t pol_out = l2_policy_evict_last();
         int chunk_no = 0;
         for (int item = group; item < n_items; item += n_groups) {
-            const int mt = (item % m_items) * tiles_per_item + rank, split = item / m_items;
-            const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+            const D16Item w = d16_item(p, item, m_items);
+            const int mt = w.m * tiles_per_item + rank, split = w.split, kb0 = w.kb0, kb1 = w.kb1;
             const int64_t grow = (int64_t)mt * kD16TileM + q * 32 + lane;        // destination row of this thread
             const int out_row = (int)(split * p.rows_per_split + (int64_t)mt * kD16TileM + q * 32);
             const bool tile_ok = mt < p.m_tiles;                                  // the odd tile out of a pair computes nothing useful
@@ -634,7 +659,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (p.selfcoef) sc = __ldg(p.selfcoef + grow);
             }
             for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb, ++chunk_no) {
-                const bool first = c0 == kb0;
+                const bool first = c0 == kb0 && (!w.add_only || kb0 == 0);     // carries the self-loop / bias terms
+                const bool store = c0 == kb0 && !w.add_only;                     // nothing to add to yet
                 mbar_wait(tmem_full, chunk_no & 1);
                 tc_fence_after();
                 // the previous chain's adds to these rows have been performed (and the staging buffers are free)
@@ -684,7 +710,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         if (p.drain_diag == 1) return;
                         if (p.drain_diag == 2) { tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out); bulk_commit_group(); return; }
 #endif
-                        if (first) tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
+                        if (store) tma_store_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
                         else tma_reduce_add_2d(&map_out, buf, cb * kD16OutCols, out_row, pol_out);
                         bulk_commit_group();
                     }
@@ -795,6 +821,7 @@ inline int d16_slots_pad(int gene_slots) { return (gene_slots + 2 * kD16TileM - 
 struct D16Plan {
     bool pair;
     int m_tiles, nb, num_kb, chunk_kb, n_splits, kb_per_split;
+    int full_items, tail_tiles, tail_splits, tail_kb;      // see D16Params
     int n_pad, n1, n2, h1, h2, b_bytes, stage_bytes, tx_bytes, stages, nbuf;
     size_t smem_bytes;
 };
@@ -802,6 +829,12 @@ struct D16Plan {
 // WSAGE_D16_PAIR=0 (env, tuning only) selects the single-CTA form
 inline bool d16_pair_env() {
     static const bool v = [] { const char* e = getenv("WSAGE_D16_PAIR"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+
+// WSAGE_D16_TAIL=0 (env, tuning only) keeps the last partial round of side-0 tiles whole
+inline bool d16_tail_env() {
+    static const bool v = [] { const char* e = getenv("WSAGE_D16_TAIL"); return !(e && atoi(e) == 0); }();
     return v;
 }
 
@@ -839,16 +872,32 @@ inline int d16_plan(const wsage_dense16_args* a, D16Plan& pl) {
     pl.b_bytes = (pl.h1 + pl.h2) * 64;
     const int tiles_per_item = pl.pair ? 2 : 1;
     const int units = pl.pair ? kNumSMs / 2 : kNumSMs;
+    pl.full_items = -1; pl.tail_tiles = pl.tail_splits = pl.tail_kb = 0;
     if (a->side == 0) {
         pl.m_tiles = (int)((a->n_dst + kD16TileM - 1) / kD16TileM);
         pl.num_kb = (a->gene_slots + kD16BlockK - 1) / kD16BlockK;
         pl.n_splits = 1;
         pl.kb_per_split = pl.num_kb;
+        // the last round of tiles is partial (c4: 2969 pairs of tiles over 74 SM pairs = 40.1 rounds, a shard of it at N = 8:
+        // 5.02): cut its tiles along k so that the round ends after 1 / tail_splits of a tile instead of a whole one
+        const int m_items = (pl.m_tiles + tiles_per_item - 1) / tiles_per_item;
+        const int chunks = (pl.num_kb + pl.chunk_kb - 1) / pl.chunk_kb;
+        const int tail = m_items % units;
+        if (d16_tail_env() && !a->deterministic && tail > 0 && chunks >= 2 && !a->relu) {
+            int ts = units / tail;
+            if (ts > chunks) ts = chunks;
+            const int cps = (chunks + ts - 1) / ts;
+            ts = (chunks + cps - 1) / cps;
+            if (ts >= 2) {
+                pl.full_items = m_items - tail; pl.tail_tiles = tail; pl.tail_splits = ts; pl.tail_kb = cps * pl.chunk_kb;
+            }
+        }
     } else {
         pl.m_tiles = d16_slots_pad(a->gene_slots) / kD16TileM;
         pl.num_kb = (int)((a->n_src_cells + kD16BlockK - 1) / kD16BlockK);
         d16_choose_splits((pl.m_tiles + tiles_per_item - 1) / tiles_per_item, units, pl.num_kb, pl.chunk_kb, pl.n_splits, pl.kb_per_split);
     }
+    if (pl.full_items < 0) pl.full_items = (pl.m_tiles + tiles_per_item - 1) / tiles_per_item * pl.n_splits;
     pl.tx_bytes = (terms == 3 ? 2 : 1) * (kD16ABytes + pl.b_bytes);
     pl.stage_bytes = (pl.tx_bytes + 1023) & ~1023;
     // staging buffers of the drain warps.  A drain of a 128 x 400 tile costs ~6.8 us (10 % of a cell-destination pass at

@@ -401,6 +401,7 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
 #endif
     p.m_tiles = pl.m_tiles; p.nb = pl.nb; p.num_kb = pl.num_kb; p.chunk_kb = pl.chunk_kb;
     p.n_splits = pl.n_splits; p.kb_per_split = pl.kb_per_split;
+    p.full_items = pl.full_items; p.tail_tiles = pl.tail_tiles; p.tail_splits = pl.tail_splits; p.tail_kb = pl.tail_kb;
     p.amax = bf ? nullptr : a->h_amax;
     p.x_amax = bf ? nullptr : a->x_amax;
     p.x_scale_inv = a->x_scale > 0.f ? 1.f / a->x_scale : 1.f;
@@ -430,7 +431,12 @@ int wsage_dense16(const wsage_dense16_args* a, void* stream) {
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles_per_item = pl.pair ? 2 : 1;
-    const int64_t items = (int64_t)((pl.m_tiles + tiles_per_item - 1) / tiles_per_item) * pl.n_splits;
+    const int64_t items = (int64_t)pl.full_items + (int64_t)pl.tail_tiles * pl.tail_splits;
+    if (pl.tail_tiles > 0) {        // the k-split tiles of the last round only ever reduce-add
+        const int64_t row0 = (int64_t)pl.full_items * tiles_per_item * kD16TileM;
+        cudaError_t e = cudaMemset2DAsync(a->out + row0 * a->ld_out, (size_t)a->ld_out * 4, 0, (size_t)a->dim * 4, (size_t)(a->n_dst - row0), st);
+        if (e != cudaSuccess) return fail(WSAGE_ECUDA, "%s: %s", "cudaMemset2DAsync(dense16 tail rows)", cudaGetErrorString(e));
+    }
     if (pl.pair) {
         auto kern = dense16_kernel<true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);

@@ -193,7 +193,7 @@ def amax_split16(x, fmt, *, row_ids=None, rowscale=None, layout=_lib.SPLIT_ROWS)
 
 
 def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, dscale=None, selfcoef=None, hself=None,
-            out=None, chunk_rows=0, src_scale=None):
+            out=None, chunk_rows=0, src_scale=None, deterministic=None):
     """The dense block's share of one pass.  side 0: returns out[n_dst, dim] (= dscale·acc + selfcoef·hself);
     side 1: returns the partial slabs [n_splits, slots_pad, dim] for ``spmm(init=...)``."""
     lib = _lib.load()
@@ -202,6 +202,8 @@ def dense16(block: DenseBlock, side: int, hs, *, n_dst=None, n_src_cells=None, d
     a = _lib.Dense16Args()
     a.x_hi, a.x_lo, a.fmt, a.cells, a.gene_slots, a.x_scale = _ptr(block.hi), _ptr(block.lo), block.fmt, block.cells, block.gene_slots, block.x_scale
     a.side, a.dim, a.chunk_rows = side, dim, chunk_rows
+    # bitwise run-to-run reproducibility of the last partial round of side-0 tiles (see wsage_dense16_args.deterministic)
+    a.deterministic = int(torch.are_deterministic_algorithms_enabled() if deterministic is None else deterministic)
     if side == 0:
         h_hi, h_lo, amax, ld = amax_split16(hs, block.fmt, row_ids=block.gene_ids, rowscale=src_scale, layout=_lib.SPLIT_KBLOCKS)
         a.n_dst = n_dst
