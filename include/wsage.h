@@ -337,7 +337,7 @@ typedef struct wsage_peer_reduce_args {
     int64_t        ld_out;
     float*         raw;          /* [rows][ld_raw] the sum itself, or NULL                               */
     int64_t        ld_raw;
-    float          timeout_s;    /* 0 = default (10 s)                                                   */
+    float          timeout_s;    /* 0 = default (60 s)                                                   */
     int32_t        grid;         /* CTAs, 0 = two per SM: all must be resident, and every call on an allocation uses the same value */
 } wsage_peer_reduce_args;
 

@@ -335,7 +335,7 @@ int wsage_peer_reduce(const wsage_peer_reduce_args* a, void* stream) {
     p.rows = a->rows; p.dim = a->dim; p.epoch = a->epoch;
     p.dscale = a->dscale; p.selfcoef = a->selfcoef; p.hself = a->hself; p.ld_hself = a->ld_hself;
     p.out = a->out; p.ld_out = a->ld_out; p.raw = a->raw; p.ld_raw = a->ld_raw;
-    p.timeout_ns = (unsigned long long)((a->timeout_s > 0.f ? a->timeout_s : 10.f) * 1e9);
+    p.timeout_ns = (unsigned long long)((a->timeout_s > 0.f ? a->timeout_s : 60.f) * 1e9);
     // two CTAs per SM, all resident: the barriers inside spin on a grid-wide counter
     peer_reduce_kernel<<<a->grid > 0 ? a->grid : 2 * kNumSMs, kPeerThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("peer_reduce");

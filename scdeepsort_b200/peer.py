@@ -20,7 +20,7 @@ def _ptr(t):
 
 
 class PeerGroup:
-    def __init__(self, rank: int, world: int, max_elems: int, bases, own_base, opened, timeout_s: float = 10.0, grid: int = 0):
+    def __init__(self, rank: int, world: int, max_elems: int, bases, own_base, opened, timeout_s: float = 60.0, grid: int = 0):
         self.rank, self.world, self.max_elems, self.timeout_s, self.grid = rank, world, int(max_elems), float(timeout_s), int(grid)
         self._bases = (c_void_p * world)(*bases)
         self._own, self._opened = own_base, opened
@@ -37,7 +37,7 @@ class PeerGroup:
         return base.value, handle.raw
 
     @classmethod
-    def create(cls, max_elems: int, group=None, timeout_s: float = 10.0) -> "PeerGroup":
+    def create(cls, max_elems: int, group=None, timeout_s: float = 60.0) -> "PeerGroup":
         """Collective over ``group`` (default: the world), all ranks on one node with peer access between their GPUs."""
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -73,7 +73,7 @@ class PeerGroup:
         return pg
 
     @classmethod
-    def local_ranks(cls, world: int, max_elems: int, timeout_s: float = 10.0):
+    def local_ranks(cls, world: int, max_elems: int, timeout_s: float = 60.0):
         """``world`` groups inside ONE process on one device (the kernels of the ranks then run side by side on separate
         streams): exercises the exchange without a second GPU.  All the ranks' CTAs must be resident together (two
         per SM fit), so each rank gets its share of the device."""
