@@ -42,7 +42,8 @@ constexpr int kD16BlockK = 32;                 // 16-bit elements per 64-byte ro
 constexpr int kD16UmmaK = 16;                  // K of one tcgen05.mma.kind::f16
 constexpr int kD16ABytes = kD16TileM * 64;     // 8 KB: one A tile (hi or lo)
 constexpr int kD16BoxMN = 32 * 64;             // 2 KB: one {32, 32} box of the MN-major operands
-constexpr int kD16Threads = 192;
+constexpr int kD16DrainWarps = 8;                     // two per TMEM lane quarter: each takes every other 16-column block
+constexpr int kD16Threads = 32 * (2 + kD16DrainWarps);
 constexpr int kD16OutCols = 16;                // fp32 columns per TMA store box (64 bytes)
 constexpr int kD16BufBytes = 32 * 64;                  // one staging buffer of a drain warp: [32 rows][64 B]
 constexpr int kD16MaxBufs = 6;                         // staging buffers per drain warp (TMA stores in flight)
@@ -466,7 +467,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     extern __shared__ unsigned char dsmem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* staging = ring + (size_t)p.stages * p.stage_bytes;          // 1024-byte aligned (stage_bytes % 1024 == 0)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * p.nbuf * kD16BufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kD16DrainWarps * p.nbuf * kD16BufBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kD16MaxStages;
     uint64_t* tmem_full = bars + 2 * kD16MaxStages;
@@ -488,7 +489,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, PAIR ? 8 : 4);
+        mbar_init(tmem_empty, PAIR ? 2 * kD16DrainWarps : kD16DrainWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -639,6 +640,8 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else {
         // ------------------------------------ drain warps -------------------------------------
         const int q = warp & 3;                                   // TMEM lane quarter of this warp
+        constexpr int kShare = kD16DrainWarps / 4;                // warps per quarter
+        const int cb_first = (warp - 2) / 4;                      // this warp's column blocks: cb_first, cb_first + kShare, ...
         unsigned char* my_stage = staging + (warp - 2) * (p.nbuf * kD16BufBytes);
         const int sw = (lane >> 1) & 3;                           // 64-byte swizzle: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
         const uint32_t tmem_empty_addr = PAIR ? mapa_u32(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
@@ -667,11 +670,11 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (lane == 0) bulk_wait_all();
                 __syncwarp();
                 // One 16-column block: scale, epilogue terms, swizzled staging, TMA store / reduce-add.
-                auto emit = [&](int cb, const uint32_t (&raw)[16]) {
+                auto emit = [&](int cb, int nth, const uint32_t (&raw)[16]) {       // nth: count of this warp's blocks so far
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * scale;
-                    if (cb >= p.nbuf) {                                  // the store issued nbuf blocks ago has read this buffer
+                    if (nth >= p.nbuf) {                                 // the store issued nbuf blocks ago has read this buffer
                         if (lane == 0) bulk_wait_read(p.nbuf - 1);
                         __syncwarp();
                     }
@@ -699,7 +702,7 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    unsigned char* buf = my_stage + (cb % p.nbuf) * kD16BufBytes;
+                    unsigned char* buf = my_stage + (nth % p.nbuf) * kD16BufBytes;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ sw) << 4)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
@@ -715,24 +718,26 @@ dense16_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         bulk_commit_group();
                     }
                 };
-                // software pipeline over the column blocks: the tcgen05.ld of block cb + 1 is in flight while block cb is staged and
-                // stored.  (A drain costs ~6.8 us per 128 x 400 tile — 10 % / 5 % of a cell- / gene-destination pass at 2048-row
-                // chains, measured by sweeping the chain length.  Neither this overlap nor more stores in flight shortens it
-                // measurably, and without any TMA traffic it still costs 2/3 of that: what remains is the tensor pipe idling
-                // through the chain hand-over, which only a second accumulator — 800 TMEM columns at N = 400 — would hide.)
+                // software pipeline over this warp's column blocks: the tcgen05.ld of the next block is in flight while a block is
+                // staged and stored.  (With four drain warps a drain cost ~6.8 us per 128 x 400 tile — 10 % / 5 % of a cell- /
+                // gene-destination pass at 2048-row chains, 80 % of a K = 400 dense-layer tile — during which the tensor pipe idles:
+                // a second accumulator would need 800 TMEM columns.  More stores in flight did not shorten it and without any TMA
+                // traffic it still cost 2/3 of that: the per-block latency chain of one warp.  Hence two warps per lane quarter.)
                 if (tile_ok) {
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
                     const int n_cb = p.n_pad / kD16OutCols;
                     uint32_t ra[16], rb[16];
-                    tmem_ld16_issue(t0, ra);
-                    for (int cb = 0; cb < n_cb; cb += 2) {
+                    if (cb_first < n_cb) tmem_ld16_issue(t0 + (uint32_t)(cb_first * kD16OutCols), ra);
+                    int nth = 0;
+                    for (int cb = cb_first; cb < n_cb; cb += 2 * kShare, nth += 2) {
+                        const int cb1 = cb + kShare, cb2 = cb + 2 * kShare;
                         tmem_ld_wait(ra);
-                        if (cb + 1 < n_cb) tmem_ld16_issue(t0 + (uint32_t)((cb + 1) * kD16OutCols), rb);
-                        emit(cb, ra);
-                        if (cb + 1 < n_cb) {
+                        if (cb1 < n_cb) tmem_ld16_issue(t0 + (uint32_t)(cb1 * kD16OutCols), rb);
+                        emit(cb, nth, ra);
+                        if (cb1 < n_cb) {
                             tmem_ld_wait(rb);
-                            if (cb + 2 < n_cb) tmem_ld16_issue(t0 + (uint32_t)((cb + 2) * kD16OutCols), ra);
-                            emit(cb + 1, rb);
+                            if (cb2 < n_cb) tmem_ld16_issue(t0 + (uint32_t)(cb2 * kD16OutCols), ra);
+                            emit(cb1, nth + 1, rb);
                         }
                     }
                 }
@@ -905,7 +910,7 @@ inline int d16_plan(const wsage_dense16_args* a, D16Plan& pl) {
     // the default stays at two buffers and the ring keeps its fifth stage.
     static const int forced = [] { const char* e = getenv("WSAGE_D16_BUFS"); return e ? atoi(e) : 0; }();
     pl.nbuf = (forced >= 2 && forced <= kD16MaxBufs) ? forced : 2;
-    const int fixed = 4 * pl.nbuf * kD16BufBytes + 256 + 1024;
+    const int fixed = kD16DrainWarps * pl.nbuf * kD16BufBytes + 256 + 1024;
     pl.stages = (kD16SmemBudget - fixed) / pl.stage_bytes;
     if (pl.stages > kD16MaxStages) pl.stages = kD16MaxStages;
     pl.smem_bytes = (size_t)pl.stages * pl.stage_bytes + fixed;
