@@ -156,8 +156,10 @@ int wsage_spmm(const wsage_spmm_args* a, void* stream);
  *                WSAGE_SPLIT_ROWS        planes [rows][ld_out]                     (ld_out % 8 == 0)
  *                WSAGE_SPLIT_TRANSPOSED  planes [cols][ld_out], the (gathered: row_ids) rows as columns
  *                WSAGE_SPLIT_COLBLOCKS   planes [ceil(cols / 32)][ld_out rows][32]: 32-column blocks of 64-byte rows
- *                WSAGE_SPLIT_BLOCKED     planes [ceil(rows / 128)][ld_out / 32][128][32], zero-filled past the matrix: the X-plane
- *                                        layout of wsage_dense16 for a dense activation / gradient matrix (ld_out = slot padding)
+ *                WSAGE_SPLIT_BLOCKED     planes [ceil(rows / 128)][ld_out / 32][128][32]: the X-plane layout of wsage_dense16 for a
+ *                                        dense activation / gradient matrix (ld_out = slot padding).  Zero-filled past the matrix
+ *                                        inside the 32-column blocks that hold columns; blocks entirely past `cols` are left
+ *                                        unwritten (no k-block of side 0 covers them, on side 1 they are output rows past the matrix)
  *                WSAGE_SPLIT_KBLOCKS     planes [ceil(rows / 32)][ld_out][32]: transposed, cut into k-blocks of 32 (gathered)
  *                                        rows — the H^T operand of wsage_dense16: one k-block of all columns is one contiguous
  *                                        piece.  Entries past `rows` in the last block are zeros; ld_out >= cols.
@@ -180,6 +182,12 @@ int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int6
                          const int32_t* row_ids, const float* rowscale,
                          int64_t rows, int32_t cols, const float* amax, int32_t fmt, int32_t layout,
                          void* hi, void* lo, int64_t ld_out, void* stream);
+/* wsage_split16_masked(layout = WSAGE_SPLIT_BLOCKED) and wsage_colsum_masked of the same x and mask in one pass over them
+ * (ABI >= 2001): the split of a layer's output gradient for its dx / dW products and its bias gradient.  partial: scratch of
+ * n_partial * cols floats (any n_partial >= 1; more rows = more CTAs, 90 are plenty), colsum: [cols]. */
+int wsage_split16_colsum(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask, int64_t rows, int32_t cols,
+                         const float* amax, int32_t fmt, void* hi, void* lo, int64_t ld_out,
+                         float* partial, int32_t n_partial, float* colsum, void* stream);
 /* Bias gradient of a Linear (+ ReLU) layer (autograd through nn.Linear's bias, models/gnn.py:13,21-22):
  * out[c] = SUM_r x[r,c] * (mask_src[r,c] > 0) (mask_src NULL: plain column sums).  partial: [n_partial][cols] scratch,
  * added in index order (deterministic).  cols % 4 == 0, cols <= 1024. */

@@ -20,7 +20,7 @@ SPLIT_ROWS, SPLIT_TRANSPOSED, SPLIT_COLBLOCKS, SPLIT_KBLOCKS, SPLIT_BLOCKED = 0,
 
 EXPORTS = ("wsage_version", "wsage_last_error", "wsage_launch_count", "wsage_block_agg_fwd",
            "wsage_block_agg_bwd", "wsage_spmm_workspace_bytes", "wsage_spmm_algo", "wsage_spmm", "wsage_amax", "wsage_split16",
-           "wsage_split16_masked", "wsage_sum_slabs", "wsage_colsum_masked", "wsage_rowdot",
+           "wsage_split16_masked", "wsage_split16_colsum", "wsage_sum_slabs", "wsage_colsum_masked", "wsage_rowdot",
            "wsage_dense16_slots_pad", "wsage_dense16_splits", "wsage_dense16",
            "wsage_split_tf32", "wsage_linear_tc", "wsage_grad_w_splits", "wsage_grad_w_tc", "wsage_sample_neighbors",
            "wsage_softmax_ce", "wsage_adam_step",
@@ -112,6 +112,9 @@ def load():
     lib.wsage_split16_masked.restype = c_int32
     lib.wsage_split16_masked.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32,
                                          c_int32, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.wsage_split16_colsum.restype = c_int32
+    lib.wsage_split16_colsum.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
+                                         c_int64, c_void_p, c_int32, c_void_p, c_void_p]
     lib.wsage_sum_slabs.restype = c_int32
     lib.wsage_sum_slabs.argtypes = [c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p]
     lib.wsage_colsum_masked.restype = c_int32

@@ -145,6 +145,96 @@ split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict_
 
 // partial[b, :] = SUM_{r in block b's rows} x[r, :] * (mask_src[r, :] > 0): the bias gradient of a Linear + ReLU layer (column sums
 // of the masked output gradient); the per-block partials are added in block order by sum_slabs_kernel (deterministic).
+// Layout 4 (BLOCKED) on its own: a work item is one (tile of 128 rows, block of 32 columns) = 8 KB contiguous per plane.
+// Thread <-> (row, 8 columns): two float4 loads (+ two of the mask), one 16-byte store per plane; a warp writes 512 contiguous
+// bytes.  gridDim.x = (column blocks in use) x groups: a CTA keeps its column block and walks the tiles group, group + groups, ...
+// Blocks entirely past `cols` are not written (side 0 never loads them, on side 1 they only feed output rows past the matrix).
+// COLSUM: also partial[group][c] = SUM over the group's rows of v[r, c] (the bias gradient of the layer whose output gradient
+// is being split: one pass over dy and the mask instead of two); fixed assignment and order, so the sums are reproducible.
+template <bool COLSUM>
+__global__ void __launch_bounds__(256)
+split16_blocked_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ mask_src, int64_t ld_m,
+                       const float* __restrict__ rowscale, int64_t rows, int cols, const float* __restrict__ amax, int fmt,
+                       unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o, float* __restrict__ partial) {
+    const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
+    const int nb = (int)(ld_o / 32), nb_used = (cols + 31) / 32;
+    const int64_t n_tiles = (rows + 127) / 128;
+    const int cb = blockIdx.x % nb_used, group = blockIdx.x / nb_used, groups = gridDim.x / nb_used;
+    const int c8 = (threadIdx.x & 3) * 8, rr = threadIdx.x >> 2;            // 4 threads per row of the block, 64 rows per sweep
+    const int c = cb * 32 + c8;
+    float sum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+    for (int64_t t = group; t < n_tiles; t += groups) {
+        float4 v[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int64_t r = t * 128 + j * 64 + rr;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                v[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows && c + 4 * k < cols) v[j][k] = __ldg(reinterpret_cast<const float4*>(x + r * ld + c + 4 * k));
+            }
+        }
+        if (mask_src) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t r = t * 128 + j * 64 + rr;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (r < rows && c + 4 * k < cols) {
+                        const float4 y = __ldg(reinterpret_cast<const float4*>(mask_src + r * ld_m + c + 4 * k));
+                        v[j][k].x = y.x > 0.f ? v[j][k].x : 0.f; v[j][k].y = y.y > 0.f ? v[j][k].y : 0.f;
+                        v[j][k].z = y.z > 0.f ? v[j][k].z : 0.f; v[j][k].w = y.w > 0.f ? v[j][k].w : 0.f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int64_t r = t * 128 + j * 64 + rr;
+            if (COLSUM) {
+                sum[0] += v[j][0].x; sum[1] += v[j][0].y; sum[2] += v[j][0].z; sum[3] += v[j][0].w;
+                sum[4] += v[j][1].x; sum[5] += v[j][1].y; sum[6] += v[j][1].z; sum[7] += v[j][1].w;
+            }
+            const float sc = scale * ((rowscale && r < rows) ? __ldg(rowscale + r) : 1.f);
+            const float f[8] = {v[j][0].x * sc, v[j][0].y * sc, v[j][0].z * sc, v[j][0].w * sc,
+                                v[j][1].x * sc, v[j][1].y * sc, v[j][1].z * sc, v[j][1].w * sc};
+            unsigned short h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d16_split(f[i], fmt, h[i], l[i]);
+            const int64_t o = (((t * nb + cb) << 7) + (j * 64 + rr)) * 32 + c8;
+            *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16),
+                                                           h[4] | ((unsigned)h[5] << 16), h[6] | ((unsigned)h[7] << 16));
+            if (fmt == 0)
+                *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16),
+                                                               l[4] | ((unsigned)l[5] << 16), l[6] | ((unsigned)l[7] << 16));
+        }
+    }
+    if (COLSUM) {
+        // lanes with equal (lane & 3) hold the same 8 columns: butterfly over the other lane bits, then the 8 warps in order
+        __shared__ float red[8][32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 4);
+            sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 8);
+            sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 16);
+        }
+        if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = sum[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && cb * 32 + threadIdx.x < cols) {
+            float a = red[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) a += red[w][threadIdx.x];
+            partial[(int64_t)group * cols + cb * 32 + threadIdx.x] = a;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 colsum_masked_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ mask_src, int64_t ld_m,
                      int64_t rows, int cols, float* __restrict__ partial) {

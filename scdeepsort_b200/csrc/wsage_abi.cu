@@ -205,12 +205,46 @@ int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int6
         split16_transpose_kernel<<<dim3(gx, gy), 128, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_KBLOCKS ? 1 : 0);
         return check_launch("split16_transpose");
     }
-    const int64_t cols_p = layout == WSAGE_SPLIT_BLOCKED ? ld_out : (cols + 31) / 32 * 32;
+    if (layout == WSAGE_SPLIT_BLOCKED) {
+        const int nb_used = (cols + 31) / 32;
+        int64_t groups = (int64_t)kNumSMs * 8 / nb_used;
+        if (groups < 1) groups = 1;
+        if (groups > (rows + 127) / 128) groups = (rows + 127) / 128;
+        const int grid = (int)(groups * nb_used);
+        split16_blocked_kernel<false><<<grid, 256, 0, st>>>(x, ld, mask_src, ld_mask, rowscale, rows, cols, amax, fmt, h, l, ld_out, nullptr);
+        return check_launch("split16_blocked");
+    }
+    const int64_t cols_p = (cols + 31) / 32 * 32;
     const int64_t total = (rows + 127) / 128 * 128 * (cols_p / 4);
     int64_t grid = (total + 255) / 256;
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
     split16_kernel<<<(int)grid, 256, 0, st>>>(x, ld, mask_src, ld_mask, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout);
     return check_launch("split16");
+}
+
+int wsage_split16_colsum(const float* x, int64_t ld, const float* mask_src, int64_t ld_mask, int64_t rows, int32_t cols,
+                         const float* amax, int32_t fmt, void* hi, void* lo, int64_t ld_out,
+                         float* partial, int32_t n_partial, float* colsum, void* stream) {
+    WSAGE_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "rows must be positive, cols a positive multiple of 4");
+    WSAGE_REQUIRE(fmt == WSAGE_D16_F16X2 || fmt == WSAGE_D16_BF16, "unknown fmt");
+    WSAGE_REQUIRE(x && hi && (lo || fmt == WSAGE_D16_BF16) && partial && colsum && n_partial >= 1, "null pointer");
+    WSAGE_REQUIRE(ld >= cols && ld % 4 == 0 && aligned16(x), "x must be 16-byte aligned with ld % 4 == 0");
+    WSAGE_REQUIRE(aligned16(hi) && aligned16(lo) && aligned16(partial) && aligned16(colsum), "outputs must be 16-byte aligned");
+    WSAGE_REQUIRE(!mask_src || (ld_mask >= cols && ld_mask % 4 == 0 && aligned16(mask_src)), "bad mask");
+    WSAGE_REQUIRE(ld_out % 32 == 0 && ld_out >= cols, "ld_out (slot padding) must be a multiple of 32, at least cols");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb_used = (cols + 31) / 32;
+    int64_t groups = (int64_t)kNumSMs * 8 / nb_used;
+    if (groups < 1) groups = 1;
+    if (groups > n_partial) groups = n_partial;
+    if (groups > (rows + 127) / 128) groups = (rows + 127) / 128;
+    split16_blocked_kernel<true><<<(int)(groups * nb_used), 256, 0, st>>>(x, ld, mask_src, ld_mask, nullptr, rows, cols, amax, fmt,
+                                                                          static_cast<unsigned short*>(hi), static_cast<unsigned short*>(lo), ld_out, partial);
+    int rc = check_launch("split16_blocked (colsum)");
+    if (rc != WSAGE_OK) return rc;
+    // the groups' sums, added in group order
+    sum_slabs_kernel<<<(cols / 4 + 255) / 256, 256, 0, st>>>(partial, (int)groups, cols, 1, cols, colsum, cols);
+    return check_launch("sum_slabs");
 }
 
 int wsage_sum_slabs(const float* slabs, int32_t n_slabs, int64_t slab_stride, int64_t rows, int32_t cols,

@@ -160,12 +160,24 @@ def _split(x, fmt, layout, ld, shape, amax, mask_src=None):
     return hi, lo
 
 
-def _planes_a(x, fmt, mask_src=None):
-    """BLOCKED planes of a [rows, k] matrix: (hi, lo, amax, rows, k)."""
+def _planes_a(x, fmt, mask_src=None, colsum=None):
+    """BLOCKED planes of a [rows, k] matrix: (hi, lo, amax, rows, k).  ``colsum`` ([k] floats): also receives the column sums
+    of x * (mask_src > 0) — the bias gradient — from the same pass."""
     rows, k = x.shape
-    pad = int(_lib.load().wsage_dense16_slots_pad(k))
+    lib = _lib.load()
+    pad = int(lib.wsage_dense16_slots_pad(k))
     amax = _amax(x, fmt)
-    hi, lo = _split(x, fmt, _lib.SPLIT_BLOCKED, pad, ((rows + 127) // 128 * pad * 128,), amax, mask_src)
+    shape = ((rows + 127) // 128 * pad * 128,)
+    if colsum is None:
+        hi, lo = _split(x, fmt, _lib.SPLIT_BLOCKED, pad, shape, amax, mask_src)
+    else:
+        hi = torch.empty(shape, device=x.device, dtype=torch.int16)
+        lo = torch.empty(shape, device=x.device, dtype=torch.int16) if fmt == _lib.D16_F16X2 else None
+        n_partial = max(1, min(148 * 8 // ((k + 31) // 32), (rows + 127) // 128))
+        partial = torch.empty(n_partial, k, device=x.device, dtype=torch.float32)
+        _lib.check(lib.wsage_split16_colsum(_ptr(x), x.stride(0), _ptr(mask_src), mask_src.stride(0) if mask_src is not None else 0,
+                                            rows, k, _ptr(amax), fmt, _ptr(hi), _ptr(lo), pad, _ptr(partial), n_partial, _ptr(colsum),
+                                            _stream()), "wsage_split16_colsum")
     return hi, lo, amax, rows, k
 
 
@@ -249,7 +261,9 @@ class _LinearReluD16(torch.autograd.Function):
         fmt = ctx.fmt
         dx = dw = db = None
         if need_x or need_w:
-            g = _planes_a(dy, fmt, mask_src=y if ctx.relu else None)          # g = dy * (y > 0), split into A planes
+            if need_b and m > 0:        # the bias gradient rides on the split's pass over dy and the mask
+                db = torch.empty(n, device=dy.device, dtype=torch.float32)
+            g = _planes_a(dy, fmt, mask_src=y if ctx.relu else None, colsum=db)  # g = dy * (y > 0), split into A planes
         if need_x:
             dx = torch.empty(m, k, device=dy.device, dtype=torch.float32)
             for k0 in range(0, k, _D16_MAX_N):
@@ -264,7 +278,7 @@ class _LinearReluD16(torch.autograd.Function):
                 slabs = _gemm16(g, _planes_b(xs, fmt, k_is_row=True, amax=x_amax), fmt, 1, k1 - k0, None)
                 _lib.check(lib.wsage_sum_slabs(_ptr(slabs), slabs.shape[0], slabs.shape[1] * slabs.shape[2], n, k1 - k0,
                                                _ptr(dw[:, k0:k1]), dw.stride(0), _stream()), "wsage_sum_slabs")
-        if need_b:
+        if need_b and db is None:
             db = colsum_masked(dy, y if ctx.relu else None)
         return dx, dw, db, None
 

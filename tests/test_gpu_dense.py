@@ -116,3 +116,31 @@ def test_colsum_masked_matches_torch_and_is_deterministic():
         assert rel_err(got.cpu(), (x.double() * (y > 0)).sum(0).cpu()) < 1e-5
         assert torch.equal(got, dense.colsum_masked(x, y))
         assert rel_err(dense.colsum_masked(x).cpu(), x.double().sum(0).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,cols", [(70000, 400), (5, 16), (1234, 132), (129, 512), (300, 36)])
+def test_blocked_split_with_fused_column_sums(rows, cols):
+    """wsage_split16_colsum: the planes are those of wsage_split16_masked (bit for bit, in every block that holds columns), decode
+    to the masked matrix within the fp16 hi+lo resolution, and the fused bias gradient equals the two-pass one's value."""
+    g = torch.Generator(device="cpu").manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, generator=g) * 3).to(DEV)
+    y = torch.randn(rows, cols, generator=g).to(DEV)
+    fmt = sd._lib.D16_F16X2
+    db = torch.full((cols,), float("nan"), device=DEV)
+    hi, lo, amax, _, _ = dense._planes_a(x, fmt, mask_src=y, colsum=db)
+    hi2, lo2, amax2, _, _ = dense._planes_a(x, fmt, mask_src=y)
+    pad = int(sd._lib.load().wsage_dense16_slots_pad(cols))
+    nb_used = (cols + 31) // 32
+    view = lambda p: p.view(-1, pad // 32, 128, 32)[:, :nb_used]
+    assert torch.equal(view(hi), view(hi2)) and torch.equal(view(lo), view(lo2)) and torch.equal(amax, amax2)
+    want = x.double() * (y > 0)
+    assert rel_err(db.cpu(), want.sum(0).cpu()) < 1e-5
+    db2 = torch.empty(cols, device=DEV)
+    dense._planes_a(x, fmt, mask_src=y, colsum=db2)
+    assert torch.equal(db, db2)                                            # fixed assignment and order
+    # decode: [tile][block][row][col] -> [rows, cols]
+    k = 14 - int(np.frexp(float(amax))[1])
+    dec = (view(hi).view(torch.float16).double() + view(lo).view(torch.float16).double()) * 2.0 ** -k
+    dec = dec.permute(0, 2, 1, 3).reshape(-1, nb_used * 32)
+    assert float((dec[:rows, :cols] - want).abs().max()) <= 2.0 ** -20 * float(amax)
+    assert float(dec[rows:].abs().max() if dec.shape[0] > rows else 0.0) == 0.0 and float(dec[:, cols:].abs().sum()) == 0.0
