@@ -67,14 +67,33 @@ amax_kernel(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__
             int64_t rows, int cols, unsigned* __restrict__ out) {
     const int64_t n4 = cols / 4;
     const int64_t total = rows * n4;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
     float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / n4;
-        const int c = (int)(i - r * n4) * 4;
-        const int64_t src = row_ids ? (int64_t)__ldg(row_ids + r) : r;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + src * ld + c));
-        const float s = rowscale ? fabsf(__ldg(rowscale + src)) : 1.f;
-        m = fmaxf(m, s * fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    if (!row_ids && !rowscale && ld == cols) {
+        // a contiguous matrix: a flat sweep, four independent 16-byte loads per thread and iteration
+        const float4* p = reinterpret_cast<const float4*>(x);
+        int64_t i = tid;
+        for (; i + 3 * nthreads < total; i += 4 * nthreads) {
+            const float4 a = __ldg(p + i), b = __ldg(p + i + nthreads), c = __ldg(p + i + 2 * nthreads), d = __ldg(p + i + 3 * nthreads);
+            const float ma = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+            const float mb = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+            const float mc = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
+            const float md = fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)));
+            m = fmaxf(m, fmaxf(fmaxf(ma, mb), fmaxf(mc, md)));
+        }
+        for (; i < total; i += nthreads) {
+            const float4 a = __ldg(p + i);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+        }
+    } else {
+        for (int64_t i = tid; i < total; i += nthreads) {
+            const int64_t r = i / n4;
+            const int c = (int)(i - r * n4) * 4;
+            const int64_t src = row_ids ? (int64_t)__ldg(row_ids + r) : r;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + src * ld + c));
+            const float s = rowscale ? fabsf(__ldg(rowscale + src)) : 1.f;
+            m = fmaxf(m, s * fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -145,6 +164,49 @@ split16_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict_
 
 // partial[b, :] = SUM_{r in block b's rows} x[r, :] * (mask_src[r, :] > 0): the bias gradient of a Linear + ReLU layer (column sums
 // of the masked output gradient); the per-block partials are added in block order by sum_slabs_kernel (deterministic).
+// The k-blocked transposition for matrices with many rows: a block owns one k-block (32 source rows), each of its warps a
+// tile of 32 columns (lane <-> column).  A thread reads its column of all 32 rows (32 loads in flight, each a warp-wide
+// 128-byte row segment) and then owns one whole 64-byte output row per plane: the warp writes 2 KB contiguous per plane
+// (split16_transpose_kernel's 16-byte pieces at a 64-byte stride: 0.65 ms for 780 k x 400; ideal 0.40).
+__global__ void __launch_bounds__(128)
+split16_kblocks_wide_kernel(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__ row_ids, const float* __restrict__ rowscale,
+                            int64_t rows, int cols, const float* __restrict__ amax, int fmt,
+                            unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int64_t ld_o) {
+    __shared__ int64_t s_src[32];
+    __shared__ float s_rs[32];
+    const float scale = (fmt == 0 && amax) ? ldexpf(1.f, d16_scale_exp(*amax)) : 1.f;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x < 32) {
+        const int64_t sidx = (int64_t)blockIdx.x * 32 + threadIdx.x;
+        const int64_t src = sidx < rows ? (row_ids ? (int64_t)__ldg(row_ids + sidx) : sidx) : -1;
+        s_src[threadIdx.x] = src;
+        s_rs[threadIdx.x] = (src >= 0 && rowscale) ? scale * __ldg(rowscale + src) : scale;
+    }
+    __syncthreads();
+    for (int c0 = w * 32; c0 < cols; c0 += 128) {
+        const int c = c0 + lane;
+        if (c >= cols) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int64_t src = s_src[i];
+            v[i] = src >= 0 ? __ldg(x + src * ld + c) * s_rs[i] : 0.f;
+        }
+        const int64_t o = ((int64_t)blockIdx.x * ld_o + c) * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            unsigned short h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d16_split(v[g * 8 + i], fmt, h[i], l[i]);
+            *reinterpret_cast<uint4*>(hi + o + g * 8) = make_uint4(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16),
+                                                                   h[4] | ((unsigned)h[5] << 16), h[6] | ((unsigned)h[7] << 16));
+            if (fmt == 0)
+                *reinterpret_cast<uint4*>(lo + o + g * 8) = make_uint4(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16),
+                                                                       l[4] | ((unsigned)l[5] << 16), l[6] | ((unsigned)l[7] << 16));
+        }
+    }
+}
+
 // Layout 4 (BLOCKED) on its own: a work item is one (tile of 128 rows, block of 32 columns) = 8 KB contiguous per plane.
 // Thread <-> (row, 8 columns): two float4 loads (+ two of the mask), one 16-byte store per plane; a warp writes 512 contiguous
 // bytes.  gridDim.x = (column blocks in use) x groups: a CTA keeps its column block and walks the tiles group, group + groups, ...

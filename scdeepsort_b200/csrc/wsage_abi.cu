@@ -202,6 +202,10 @@ int wsage_split16_masked(const float* x, int64_t ld, const float* mask_src, int6
         // few source rows (a weight matrix): spread the column tiles over blocks too; many: one block per 32 rows walks all of them
         const unsigned gx = (unsigned)((rows + 31) / 32);
         const unsigned gy = gx >= 4u * kNumSMs ? 1u : (unsigned)((cols + 31) / 32);
+        if (layout == WSAGE_SPLIT_KBLOCKS && gy == 1u) {
+            split16_kblocks_wide_kernel<<<gx, 128, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out);
+            return check_launch("split16_kblocks_wide");
+        }
         split16_transpose_kernel<<<dim3(gx, gy), 128, 0, st>>>(x, ld, row_ids, rowscale, rows, cols, amax, fmt, h, l, ld_out, layout == WSAGE_SPLIT_KBLOCKS ? 1 : 0);
         return check_launch("split16_transpose");
     }

@@ -40,3 +40,6 @@ bw = dense._planes_b(w.detach(), fmt, k_is_row=False)
 out = torch.empty(rows, n, device="cuda")
 print(f"dense16 GEMM alone (planes ready): {timed(lambda: dense._gemm16(a, bw, fmt, 0, n, out, bias=b.detach(), relu=True)):.3f} ms", flush=True)
 print(f"split BLOCKED(x): {timed(lambda: dense._planes_a(x, fmt)):.3f} ms;  KBLOCKS(x): {timed(lambda: dense._planes_b(x, fmt, k_is_row=True)):.3f} ms", flush=True)
+am = dense._amax(x, fmt)
+print(f"amax(x): {timed(lambda: dense._amax(x, fmt)):.3f} ms;  KBLOCKS(x) with amax given: {timed(lambda: dense._planes_b(x, fmt, k_is_row=True, amax=am)):.3f} ms "
+      f"(ideal at 6.4 TB/s: 0.19 / 0.40 ms)", flush=True)
