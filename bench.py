@@ -33,8 +33,9 @@ NUM_CLASSES = 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="default 5 (full-graph step), 30 (sampled mini-batches)")
+    ap.add_argument("--warmup", type=int, default=None, help="default 3 (full-graph step), 10 (sampled: batch shapes vary, the allocator "
+                    "needs a few batches to stop calling cudaMalloc)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=760_000)
     ap.add_argument("--genes", type=int, default=20_000)
@@ -60,6 +61,10 @@ def parse():
     ap.add_argument("--fanouts", default="25,10,5", help="sampled mode: per-hop fan-outs, seed hop first")
     ap.add_argument("--batch", type=int, default=1024, help="sampled mode: seed cells per GPU per step")
     a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 30 if a.mode == "sampled" else 5
+    if a.warmup is None:
+        a.warmup = 10 if a.mode == "sampled" else 3
     if a.config == "c3":
         a.cells, a.genes, a.deg, a.dim, a.hidden, a.dense_fmt = 100_000, 20_000, 2000.0, 400, 400, "bf16"
     elif a.config == "c1":
@@ -496,7 +501,7 @@ def run_sampled(a):
         loss.backward()
         parallel.allreduce_grads(model)
         opt.step()
-        return float(loss)                                                           # D2H: loss.item()
+        return float(loss.detach())                                                           # D2H: loss.item()
 
     e2e_step(0)
     if world > 1:

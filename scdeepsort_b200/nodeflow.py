@@ -79,7 +79,7 @@ def _sample_edges_cuda(g: DeepSortGraph, nodes: torch.Tensor, fanout: int, seed:
     lib = _lib.load()
     p = lambda t: ctypes.c_void_p(t.data_ptr())      # noqa: E731
     _lib.check(lib.wsage_sample_neighbors(p(g.in_rowptr), p(nodes), n, fanout, ctypes.c_uint64(seed & (2 ** 64 - 1)),
-                                          p(eid), p(deg), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                                          p(eid), p(deg), ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))),
                "wsage_sample_neighbors")
     deg = deg.to(torch.int64)
     keep = torch.arange(fanout, device=nodes.device)[None, :] < deg[:, None]

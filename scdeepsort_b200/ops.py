@@ -16,7 +16,8 @@ TIMING = None     # set to a list by bench.py to collect per-launch CUDA-event t
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # the raw handle of torch's current stream: ~0.3 us, against ~10 us for torch.cuda.current_stream() (95 calls per sampled step)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _timed(record, fn):
