@@ -387,3 +387,16 @@ def test_peer_reduce_rejects_bad_arguments_before_touching_the_device():
     assert lib.wsage_peer_reduce(ctypes.byref(a), None) == sd._lib.EINVAL and b"epoch" in lib.wsage_last_error()
     a.epoch = 3
     assert lib.wsage_peer_reduce(ctypes.byref(a), None) == sd._lib.EINVAL and b"null" in lib.wsage_last_error()
+
+
+def test_peer_exchange_is_off_without_a_process_group_or_a_gpu():
+    """parallel.enable_peer_exchange / peer.enable are collective set-up calls: outside torch.distributed, or for a graph that
+    is not on a GPU, they leave the NCCL / gloo all-reduce in place and say so by returning None."""
+    from scdeepsort_b200 import parallel, peer
+    from scdeepsort_b200.synthetic import synthetic_bipartite
+    bg = synthetic_bipartite(60, 40, 8, device="cpu")
+    assert parallel.enable_peer_exchange(bg, 64) is None and bg.peer_group is None
+    assert peer.enable(1000) is None and peer.active() is None
+    peer.disable()                                    # nothing to tear down: a no-op
+    header = (ROOT / "include" / "wsage.h").read_text()
+    assert f"#define WSAGE_PEER_MAX {sd._lib.PEER_MAX}" in header
